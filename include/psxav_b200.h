@@ -1,0 +1,247 @@
+/*
+ * psxav_b200.h — C ABI of libpsxav_b200.so, the B200 (sm_100a) MDEC/BS + SPU/XA-ADPCM encode
+ * core. Plain C: pointers, ints and sizes only.
+ *
+ * Two layers:
+ *
+ *  1. DROP-IN symbols with the reference's exact names, signatures and struct layouts, so
+ *     psxavenc's container/muxing layer (psxavenc/filefmt.c, libpsxav/cdrom.c) links
+ *     against this library instead of psxavenc/mdec.c + libpsxav/adpcm.c without edits.
+ *     Each declaration cites the reference declaration it replaces.
+ *
+ *  2. BATCHED entry points (psxb200_*), additive: many frames / many independent ADPCM
+ *     streams per call, device-resident or host buffers. The drop-in symbols are thin
+ *     wrappers over these with a batch of one.
+ *
+ * There is no CPU fallback: every entry point needs a CUDA device and aborts with a message
+ * on a CUDA error (the reference API has no error channel: encode_frame_bs is void,
+ * mdec.h:67; the audio functions return byte counts, libpsxav.h:79-101).
+ *
+ * All file:line citations are relative to the reference tree (WonderfulToolchain/psxavenc).
+ */
+#ifndef PSXAV_B200_H
+#define PSXAV_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===================================================================================== */
+/* 1. Drop-in layer                                                                       */
+/* ===================================================================================== */
+
+#ifndef PSXAV_B200_NO_DROPIN_TYPES
+
+/* psxavenc/args.h:45-57 */
+typedef enum {
+	FORMAT_INVALID = -1,
+	FORMAT_XA, FORMAT_XACD, FORMAT_SPU, FORMAT_VAG, FORMAT_SPUI, FORMAT_VAGI,
+	FORMAT_STR, FORMAT_STRCD, FORMAT_STRSPU, FORMAT_STRV, FORMAT_SBS
+} format_t;
+
+/* psxavenc/args.h:60-65 */
+typedef enum {
+	BS_CODEC_INVALID = -1,
+	BS_CODEC_V2, BS_CODEC_V3, BS_CODEC_V3DC
+} bs_codec_t;
+
+/* psxavenc/mdec.h:32-55. Same field order, types and offsets. The caller owns the struct
+ * (on its stack, not zeroed: filefmt.c:424,546,634) and sets frame_output, frame_max_size,
+ * frame_index, frame_data_offset, the overflow accumulators and quant_scale_sum itself
+ * after init (filefmt.c:428-440, 637-640). The five pointer fields at the end are private
+ * to the encoder in the reference as well; this library keeps its GPU context in
+ * `dct_context` (an AVDCT* in the reference) and leaves the others NULL. */
+typedef struct {
+	int frame_index;
+	int frame_data_offset;
+	int frame_max_size;
+	int frame_block_base_overflow;
+	int frame_block_overflow_num;
+	int frame_block_overflow_den;
+	int block_type;
+	int16_t last_dc_values[3];
+	uint16_t bits_value;
+	int bits_left;
+	uint8_t *frame_output;
+	int bytes_used;
+	int blocks_used;
+	int uncomp_hwords_used;
+	int quant_scale;
+	int quant_scale_sum;
+
+	void *dct_context;          /* reference: AVDCT*; here: psxb200_bs_encoder_t* */
+	uint32_t *ac_huffman_map;   /* unused (NULL) */
+	uint32_t *dc_huffman_map;   /* unused (NULL) */
+	int16_t *coeff_clamp_map;   /* unused (NULL) */
+	int16_t *dct_block_lists[6];/* unused (NULL) */
+} mdec_encoder_state_t;
+
+/* psxavenc/mdec.h:57-63 */
+typedef struct {
+	bs_codec_t video_codec;
+	int video_width;
+	int video_height;
+	mdec_encoder_state_t state;
+} mdec_encoder_t;
+
+/* psxavenc/mdec.h:65 (mdec.c:512). Allocates the GPU context; false on failure. */
+bool init_mdec_encoder(mdec_encoder_t *encoder, bs_codec_t video_codec, int video_width, int video_height);
+/* psxavenc/mdec.h:66 (mdec.c:553) */
+void destroy_mdec_encoder(mdec_encoder_t *encoder);
+/* psxavenc/mdec.h:67 (mdec.c:580). video_frame: one NV21 frame in HOST memory. Writes
+ * state.frame_output[0..frame_max_size), bytes_used, blocks_used, uncomp_hwords_used,
+ * quant_scale and adds to quant_scale_sum. Aborts when no quant scale fits (mdec.c:723). */
+void encode_frame_bs(mdec_encoder_t *encoder, const uint8_t *video_frame);
+/* psxavenc/mdec.h:68-74 (mdec.c:757). One 2016-byte slice + 32-byte STR header per call;
+ * returns the number of frames consumed from video_frames. */
+int encode_sector_str(mdec_encoder_t *encoder, format_t format, uint16_t str_video_id,
+                      const uint8_t *video_frames, uint8_t *output);
+
+/* libpsxav/libpsxav.h:31-32 */
+#define PSX_AUDIO_SPU_BLOCK_SIZE        16
+#define PSX_AUDIO_SPU_SAMPLES_PER_BLOCK 28
+/* libpsxav/libpsxav.h:34-37 */
+enum { PSX_AUDIO_XA_FREQ_SINGLE = 18900, PSX_AUDIO_XA_FREQ_DOUBLE = 37800 };
+/* libpsxav/libpsxav.h:39-42 */
+typedef enum { PSX_AUDIO_XA_FORMAT_XA, PSX_AUDIO_XA_FORMAT_XACD } psx_audio_xa_format_t;
+/* libpsxav/libpsxav.h:44-51 */
+typedef struct {
+	psx_audio_xa_format_t format;
+	bool stereo;
+	int frequency;
+	int bits_per_sample;
+	int file_number;
+	int channel_number;
+} psx_audio_xa_settings_t;
+/* libpsxav/libpsxav.h:53-57 */
+typedef struct {
+	int qerr;
+	uint64_t mse;
+	int prev1, prev2;
+} psx_audio_encoder_channel_state_t;
+/* libpsxav/libpsxav.h:59-62 */
+typedef struct {
+	psx_audio_encoder_channel_state_t left;
+	psx_audio_encoder_channel_state_t right;
+} psx_audio_encoder_state_t;
+/* libpsxav/libpsxav.h:64-71 */
+enum {
+	PSX_AUDIO_SPU_LOOP_END    = (1 << 0),
+	PSX_AUDIO_SPU_LOOP_REPEAT = (1 << 0) | (1 << 1),
+	PSX_AUDIO_SPU_LOOP_START  = (1 << 1) | (1 << 2),
+	PSX_AUDIO_SPU_LOOP_TRAP   = (1 << 0) | (1 << 2)
+};
+
+/* libpsxav/libpsxav.h:73-77 (adpcm.c:235-260): pure size arithmetic, host only. */
+uint32_t psx_audio_xa_get_buffer_size(psx_audio_xa_settings_t settings, int sample_count);
+uint32_t psx_audio_spu_get_buffer_size(int sample_count);
+uint32_t psx_audio_xa_get_buffer_size_per_sector(psx_audio_xa_settings_t settings);
+uint32_t psx_audio_xa_get_samples_per_sector(psx_audio_xa_settings_t settings);
+uint32_t psx_audio_xa_get_sector_interleave(psx_audio_xa_settings_t settings);
+/* libpsxav/libpsxav.h:78-85 (adpcm.c:293). HOST pointers; the ADPCM search runs on the GPU,
+ * sector framing / EDC on the host exactly as adpcm.c:262-332 + cdrom.c do. */
+int psx_audio_xa_encode(psx_audio_xa_settings_t settings, psx_audio_encoder_state_t *state,
+                        const int16_t *samples, int sample_count, int lba, uint8_t *output);
+/* libpsxav/libpsxav.h:86-92 (adpcm.c:342) */
+int psx_audio_xa_encode_simple(psx_audio_xa_settings_t settings, const int16_t *samples,
+                               int sample_count, int lba, uint8_t *output);
+/* libpsxav/libpsxav.h:93-99 (adpcm.c:356) */
+int psx_audio_spu_encode(psx_audio_encoder_channel_state_t *state, const int16_t *samples,
+                         int sample_count, int pitch, uint8_t *output);
+/* libpsxav/libpsxav.h:100 (adpcm.c:378) */
+int psx_audio_spu_encode_simple(const int16_t *samples, int sample_count, uint8_t *output, int loop_start);
+/* libpsxav/libpsxav.h:101 (adpcm.c:334) */
+void psx_audio_xa_encode_finalize(psx_audio_xa_settings_t settings, uint8_t *output, int output_length);
+
+#endif /* PSXAV_B200_NO_DROPIN_TYPES */
+
+/* ===================================================================================== */
+/* 2. Batched layer                                                                       */
+/* ===================================================================================== */
+
+/* Which FFmpeg AVDCT.fdct the output must match bit-for-bit:
+ * ISLOW = ff_jpeg_fdct_islow_8 (the reference's official release binaries, non-x86 builds),
+ * SSE2  = ff_fdct_sse2 (a stock SIMD-enabled x86-64 FFmpeg). Default for the drop-in layer:
+ * ISLOW, override with the environment variable PSXB200_FDCT=sse2. */
+enum { PSXB200_FDCT_ISLOW = 0, PSXB200_FDCT_SSE2 = 1 };
+
+typedef struct {
+	int bytes_used;          /* mdec.c:736; 0 when the frame failed */
+	int blocks_used;         /* mdec.c:733 */
+	int quant_scale;         /* 1..63; 64 = no quant scale fits (reference asserts, mdec.c:723) */
+	int uncomp_hwords_used;  /* mdec.c:726 */
+} psxb200_bs_result_t;
+
+typedef struct psxb200_bs_encoder psxb200_bs_encoder_t;
+
+/* Returns the CUDA device count (0 = none), without touching any device. */
+int psxb200_device_count(void);
+/* Last error message of the calling thread ("" if none). */
+const char *psxb200_last_error(void);
+
+/* codec: 0 = BS v2, 1 = v3, 2 = v3dc (bs_codec_t). width/height multiples of 16
+ * (mdec.c:601-602). max_batch: frames per internal launch (scratch is sized for it).
+ * Uses the current CUDA device. NULL on failure. */
+psxb200_bs_encoder_t *psxb200_bs_create(int codec, int width, int height, int fdct_variant, int max_batch);
+void psxb200_bs_destroy(psxb200_bs_encoder_t *enc);
+
+/* Device-resident batch: d_frames = n NV21 frames back to back (1.5*W*H bytes each, base
+ * 16-byte aligned), d_max_sizes[n] = per-frame byte budgets (frame_max_size), each
+ * <= max_size_bound; d_out = n bitstream buffers out_stride bytes apart (out_stride and
+ * base multiples of 4, out_stride >= max_size_bound); d_results[n]. Asynchronous on
+ * `stream` (a cudaStream_t, NULL = default stream). Returns 0, or -1 (see
+ * psxb200_last_error). Frames for which no quant scale fits get quant_scale 64,
+ * bytes_used 0 and an all-zero buffer. */
+int psxb200_bs_encode_device(psxb200_bs_encoder_t *enc, int n, const uint8_t *d_frames,
+                             const int *d_max_sizes, int max_size_bound, uint8_t *d_out,
+                             size_t out_stride, psxb200_bs_result_t *d_results, void *stream);
+
+/* Same with HOST buffers: copies in, encodes and copies out in pipelined chunks on the
+ * encoder's own streams; synchronous. Pinned host memory is used in place; pageable memory
+ * goes through the driver's staging. Returns the number of frames that failed (0 = all
+ * good) or -1 on error. */
+int psxb200_bs_encode_host(psxb200_bs_encoder_t *enc, int n, const uint8_t *h_frames,
+                           const int *h_max_sizes, uint8_t *h_out, size_t out_stride,
+                           psxb200_bs_result_t *h_results);
+
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+unsigned long long psxb200_launch_count(void);
+
+/* SPU-ADPCM, n_streams independent mono chains (adpcm.c:356-376 each).
+ * Stream s reads sample i at d_samples[(s / pitch) * group_stride + (s % pitch) + i * pitch]
+ * i.e. `pitch` interleaved channels per group of streams, groups group_stride samples
+ * apart (pitch 1: stream s starts at s * group_stride). sample_count samples per stream
+ * (d_counts[s] overrides when non-NULL). d_states[n_streams]: in/out, layout of
+ * psx_audio_encoder_channel_state_t. Output: 16 bytes per 28 samples at
+ * d_out + s * out_stride. Asynchronous on `stream`. Returns 0 / -1. */
+int psxb200_spu_encode_device(int n_streams, const int16_t *d_samples, int pitch, long group_stride,
+                              int sample_count, const int *d_counts, void *d_states,
+                              uint8_t *d_out, long out_stride, void *stream);
+int psxb200_spu_encode_host(int n_streams, const int16_t *h_samples, int pitch, long group_stride,
+                            int sample_count, void *h_states, uint8_t *h_out, long out_stride);
+
+/* XA-ADPCM, n_streams independent XA streams (adpcm.c:293-332 each, incl. subheaders,
+ * sound-group header duplication and EDC). Stream s reads sample_count per-channel frames
+ * (interleaved L,R when stereo) at d_samples + s * in_stride (in int16 units; readable up
+ * to the end of the last 224/112-sample sound group the reference would touch) and writes
+ * sectors of 2336 (format 0) or 2352 (format 1) bytes at d_out + s * out_stride, first
+ * sector numbered lba. d_states[n_streams][2] (left, right) in/out. Output buffers must be
+ * zero-initialised for format 0 (the reference ORs into the coding byte, adpcm.c:278-288).
+ * Returns bytes per stream (>= 0) or -1. */
+int psxb200_xa_encode_device(int n_streams, int format, int stereo, int frequency, int bits_per_sample,
+                             int file_number, int channel_number, const int16_t *d_samples,
+                             long in_stride, int sample_count, int lba, void *d_states,
+                             uint8_t *d_out, long out_stride, void *stream);
+int psxb200_xa_encode_host(int n_streams, int format, int stereo, int frequency, int bits_per_sample,
+                           int file_number, int channel_number, const int16_t *h_samples,
+                           long in_stride, int sample_count, int lba, void *h_states,
+                           uint8_t *h_out, long out_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

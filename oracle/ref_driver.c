@@ -121,3 +121,6 @@ int ref_str_encode(void *h, int format, int video_id, const uint8_t *frames, int
 	}
 	return used;
 }
+
+#include <stddef.h>
+size_t ref_sizeof_mdec_encoder(void) { return sizeof(mdec_encoder_t); }

@@ -1,0 +1,361 @@
+// SPU / XA ADPCM predictor search for sm_100a — the GPU side of psx_audio_spu_encode and
+// psx_audio_xa_encode (reference libpsxav/adpcm.c:39-233, 293-376).
+//
+// A channel is a strictly sequential chain: every 28-sample unit starts from the decoded
+// last two samples of the winning candidate of the previous unit (adpcm.c:135-136,186-190).
+// Parallelism therefore comes from (a) the candidates of one unit — filters x {m-1,m,m+1}
+// shifts, <= 15 — which run in the 16 lanes of a half-warp and are reduced with a shuffle
+// arg-min, and (b) independent chains (channels / streams), two per warp.
+//
+//   adpcm_spu_kernel   half-warp per SPU stream; 16 output bytes per unit (adpcm.c:356-376)
+//   adpcm_xa_kernel    warp per XA stream (half-warp 0 = left/mono, 1 = right); sound groups
+//                      are assembled in shared memory and stored as one 128-byte row
+//                      (encode_block_xa, adpcm.c:193-233; header duplication :321-322)
+//   xa_frame_kernel    sector sync/header/subheader (adpcm.c:266-291, cdrom.c:55-74) and the
+//                      EDC CRC (cdrom.c:30-41, 102-109), one thread per sector
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "adpcm_encode.h"
+
+namespace psxb200 {
+
+constexpr int UNIT = 28;
+
+struct ChannelState {   // psx_audio_encoder_channel_state_t (libpsxav.h:53-57)
+	int qerr;
+	int pad_;
+	unsigned long long mse;
+	int prev1, prev2;
+};
+static_assert(sizeof(ChannelState) == 24, "state layout");
+
+__device__ __forceinline__ int filter_k1(int f) { return f == 0 ? 0 : f == 1 ? 60 : f == 2 ? 115 : f == 3 ? 98 : 122; }
+__device__ __forceinline__ int filter_k2(int f) { return f < 2 ? 0 : f == 2 ? -52 : f == 3 ? -55 : -60; }
+
+__device__ __forceinline__ int bit_length(uint32_t v) { return 32 - __clz(v); }
+
+// One unit, one candidate per lane of a half-warp. `sub` = lane & 15.
+// On return every lane of the half-warp holds the winner's decoder state in (p1, p2), its
+// error in `mse` and the header byte; `mine` tells whether this lane is the winner, whose
+// `codes` (28 nibbles or bytes, sample 0 in the low bits of codes[0]) are the unit's data.
+template <int FILTERS, int RANGE>
+__device__ __forceinline__ void encode_unit(const int (&s)[UNIT], int qerr, int &p1, int &p2, int sub,
+                                            uint32_t (&codes)[RANGE == 12 ? 4 : 7], unsigned long long &mse,
+                                            int &header, bool &mine) {
+	constexpr int LO = -0x8000 >> RANGE, HI = 0x7FFF >> RANGE;
+	constexpr int KEEP = 16 - RANGE - 1;         // magnitude bits that fit without shifting
+	constexpr int BITS = 16 - RANGE;             // code width
+	constexpr uint32_t MASK = 0xFFFFu >> RANGE;
+
+	const int filter = sub / 3, which = sub - 3 * filter;
+	const bool has_candidate = filter < FILTERS;
+	const int k1 = filter_k1(has_candidate ? filter : 0), k2 = filter_k2(has_candidate ? filter : 0);
+
+	// find_min_shift (adpcm.c:39-79): open-loop residual range over the raw samples
+	int lo = 0, hi = 0;
+	{
+		int q1 = p1, q2 = p2;
+#pragma unroll
+		for (int i = 0; i < UNIT; i++) {
+			int r = s[i] - ((k1 * q1 + k2 * q2 + 32) >> 6);
+			lo = min(lo, r);
+			hi = max(hi, r);
+			q2 = q1;
+			q1 = s[i];
+		}
+	}
+	int rs = max(bit_length((uint32_t)hi), bit_length((uint32_t)max(~lo, 0))) - KEEP;
+	rs = min(max(rs, 0), RANGE);
+	const int shift = RANGE - rs + which - 1;    // candidates m-1, m, m+1 (adpcm.c:161-167)
+	const bool valid = has_candidate && shift >= 0 && shift <= RANGE;
+	const int sh = min(max(shift, 0), RANGE);
+
+	// attempt_to_encode (adpcm.c:81-140): closed-loop trial
+	int t1 = p1, t2 = p2;
+	unsigned long long err2 = 0;
+#pragma unroll
+	for (int j = 0; j < (RANGE == 12 ? 4 : 7); j++) codes[j] = 0;
+#pragma unroll
+	for (int i = 0; i < UNIT; i++) {
+		int want = s[i] + qerr;
+		int pred = (k1 * t1 + k2 * t2 + 32) >> 6;
+		int e = (((want - pred) << sh) + (1 << (RANGE - 1))) >> RANGE;
+		e = min(max(e, LO), HI);
+		int dec = (e << (RANGE - sh)) + pred;
+		dec = min(max(dec, -0x8000), 0x7FFF);
+		int d = dec - want;
+		err2 += (unsigned long long)((long long)d * d);
+		codes[(i * BITS) >> 5] |= ((uint32_t)e & MASK) << ((i * BITS) & 31);
+		t2 = t1;
+		t1 = dec;
+	}
+
+	// arg-min with first-wins ties in (filter, shift) order == lane order (adpcm.c:177-181)
+	unsigned long long key = valid ? ((err2 << 4) | (unsigned)sub) : ~0ull;
+	unsigned long long best = key;
+#pragma unroll
+	for (int o = 8; o > 0; o >>= 1) {
+		unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best, o, 16);
+		best = other < best ? other : best;
+	}
+	const int winner = (int)(best & 15);
+	mine = sub == winner;
+	mse = best >> 4;
+	p1 = __shfl_sync(0xFFFFFFFFu, t1, winner, 16);
+	p2 = __shfl_sync(0xFFFFFFFFu, t2, winner, 16);
+	header = __shfl_sync(0xFFFFFFFFu, (sh & 0x0F) | (filter << 4), winner, 16);
+}
+
+__device__ __forceinline__ void load_unit(const int16_t *__restrict__ src, long pitch, int limit, int (&s)[UNIT]) {
+#pragma unroll
+	for (int i = 0; i < UNIT; i++) s[i] = i < limit ? (int)__ldg(src + i * pitch) : 0;
+}
+
+// ---- SPU ---------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(ADPCM_THREADS)
+adpcm_spu_kernel(int n_streams, const int16_t *__restrict__ samples, int pitch, long group_stride, int sample_count,
+                 const int *__restrict__ counts, ChannelState *__restrict__ states, uint8_t *__restrict__ out,
+                 long out_stride) {
+	const int lane = threadIdx.x & 31, sub = lane & 15;
+	const int stream = (int)(((long)blockIdx.x * ADPCM_THREADS + threadIdx.x) >> 4);
+	const bool live = stream < n_streams;
+	const int count = live ? (counts ? counts[stream] : sample_count) : 0;
+	const int units = (count + UNIT - 1) / UNIT;
+	// both half-warps of a warp iterate together
+	const int warp_units = max(units, __shfl_xor_sync(0xFFFFFFFFu, units, 16));
+
+	const int16_t *src = samples;
+	ChannelState st{0, 0, 0, 0, 0};
+	if (live) {
+		src += (long)(stream / pitch) * group_stride + (stream % pitch);
+		st = states[stream];
+	}
+	int p1 = st.prev1, p2 = st.prev2;
+	unsigned long long mse = st.mse;
+	uint8_t *dst = out + (long)(live ? stream : 0) * out_stride;
+
+	for (int u = 0; u < warp_units; u++) {
+		const bool active = u < units;
+		int s[UNIT];
+		load_unit(src + (long)u * UNIT * pitch, pitch, active ? count - u * UNIT : 0, s);
+		uint32_t codes[4];
+		unsigned long long m;
+		int header;
+		bool mine;
+		int n1 = p1, n2 = p2;
+		encode_unit<5, 12>(s, st.qerr, n1, n2, sub, codes, m, header, mine);
+		if (active) {
+			p1 = n1; p2 = n2; mse = m;
+			if (mine) {
+				// header, flags = 0, 14 bytes of nibble pairs, low nibble first (adpcm.c:367-372)
+				uint4 blk;
+				blk.x = (uint32_t)header | (codes[0] << 16);
+				blk.y = (codes[0] >> 16) | (codes[1] << 16);
+				blk.z = (codes[1] >> 16) | (codes[2] << 16);
+				blk.w = (codes[2] >> 16) | (codes[3] << 16);
+				*reinterpret_cast<uint4 *>(dst + 16L * u) = blk;
+			}
+		}
+	}
+	if (live && sub == 0 && units > 0) {
+		st.prev1 = p1; st.prev2 = p2; st.mse = mse;
+		states[stream] = st;
+	}
+}
+
+// ---- XA ----------------------------------------------------------------------------------
+
+template <int BITS>   // 4 or 8
+__global__ void __launch_bounds__(ADPCM_THREADS)
+adpcm_xa_kernel(int n_streams, int stereo, int sector_size, const int16_t *__restrict__ samples, long in_stride,
+                int sample_count, ChannelState *__restrict__ states, uint8_t *__restrict__ out, long out_stride) {
+	constexpr int RANGE = BITS == 4 ? 12 : 8;
+	constexpr int UNITS = BITS == 4 ? 8 : 4;        // units per 128-byte sound group
+	constexpr int JUMP = BITS == 4 ? 224 : 112;     // interleaved samples per sound group
+	constexpr int WARPS = ADPCM_THREADS / 32;
+	__shared__ uint8_t stage[WARPS][UNITS][32];     // unit codes, one byte per sample
+	__shared__ uint8_t hdrs[WARPS][UNITS];
+
+	const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4, wslot = threadIdx.x >> 5;
+	const int stream = blockIdx.x * WARPS + wslot;
+	if (stream >= n_streams) return;
+
+	const int16_t *base = samples + (long)stream * in_stride;
+	const int total = stereo ? sample_count * 2 : sample_count;
+	const int groups = ((total + JUMP - 1) / JUMP + 17) / 18 * 18;   // padded to whole sectors (adpcm.c:310)
+	// half-warp 0 drives left/mono, half-warp 1 the right channel (idle when mono)
+	ChannelState st = states[(long)stream * 2 + (stereo ? half : 0)];
+	int p1 = st.prev1, p2 = st.prev2;
+	unsigned long long mse = st.mse;
+	const bool chain = stereo || half == 0;
+	const int steps = stereo ? UNITS / 2 : UNITS;   // sequential units per chain per group
+
+	for (int j = 0; j < groups; j++) {
+		const int16_t *gsrc = base + (long)j * JUMP;
+		const int limit0 = total - j * JUMP;
+		for (int step = 0; step < steps; step++) {
+			// stereo: pointer advances 56 interleaved samples per L/R pair but the limit only
+			// drops by 28 (adpcm.c:204-211); mono: 28 and 28
+			const int16_t *src = stereo ? gsrc + 56 * step + half : gsrc + 28 * step;
+			const int unit = stereo ? 2 * step + half : step;
+			int s[UNIT];
+			load_unit(src, stereo ? 2 : 1, chain ? limit0 - 28 * step : 0, s);
+			uint32_t codes[BITS == 4 ? 4 : 7];
+			unsigned long long m;
+			int header;
+			bool mine;
+			int n1 = p1, n2 = p2;
+			encode_unit<4, RANGE>(s, st.qerr, n1, n2, sub, codes, m, header, mine);
+			if (chain) {
+				p1 = n1; p2 = n2; mse = m;
+				if (mine) {
+					hdrs[wslot][unit] = (uint8_t)header;
+#pragma unroll
+					for (int i = 0; i < UNIT; i++)
+						stage[wslot][unit][i] = (uint8_t)((codes[(i * BITS) >> 5] >> ((i * BITS) & 31)) & (BITS == 4 ? 0xF : 0xFF));
+				}
+			}
+		}
+		__syncwarp();
+		// assemble the 128-byte sound group: words 0-3 headers (with duplicates), 4-31 data rows
+		uint32_t word;
+		if (lane < 4) {
+			if (BITS == 4) {
+				int h = (lane >> 1) * 4;   // words 0,1 <- units 0-3; words 2,3 <- units 4-7
+				word = hdrs[wslot][h] | (hdrs[wslot][h + 1] << 8) | (hdrs[wslot][h + 2] << 16) | (hdrs[wslot][h + 3] << 24);
+			} else {
+				// 8-bit: bytes 0-3 = unit headers, copied to 4-7; bytes 8-15 keep the caller's
+				// content in the reference (copied 8-11 -> 12-15, adpcm.c:322) and are
+				// written as zero here (the batch API requires zeroed output buffers).
+				word = lane < 2 ? (hdrs[wslot][0] | (hdrs[wslot][1] << 8) | (hdrs[wslot][2] << 16) | (hdrs[wslot][3] << 24)) : 0u;
+			}
+		} else {
+			int i = lane - 4;
+			if (BITS == 4) {
+				word = 0;
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+					word |= (uint32_t)(stage[wslot][2 * k][i] | (stage[wslot][2 * k + 1][i] << 4)) << (8 * k);
+			} else {
+				word = stage[wslot][0][i] | (stage[wslot][1][i] << 8) | (stage[wslot][2][i] << 16) | (stage[wslot][3][i] << 24);
+			}
+		}
+		uint8_t *sec = out + (long)stream * out_stride + (long)(j / 18) * sector_size - (2352 - sector_size);
+		uint8_t *grp = sec + 24 + (j % 18) * 128;
+		if (BITS == 8 && lane >= 2 && lane < 4) {
+			// leave bytes 8-15 of 8-bit groups exactly as the reference does: 12-15 := 8-11
+			if (lane == 3) {
+				uint32_t keep = *reinterpret_cast<const uint32_t *>(grp + 8);
+				*reinterpret_cast<uint32_t *>(grp + 12) = keep;
+			}
+		} else {
+			*reinterpret_cast<uint32_t *>(grp + 4 * lane) = word;
+		}
+		__syncwarp();
+	}
+	if (chain && sub == 0 && groups > 0) {
+		st.prev1 = p1; st.prev2 = p2; st.mse = mse;
+		states[(long)stream * 2 + (stereo ? half : 0)] = st;
+	}
+}
+
+// ---- XA sector framing + EDC -------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t edc_step(uint32_t crc, uint32_t byte, const uint32_t *tab) {
+	return (crc >> 8) ^ tab[(crc ^ byte) & 0xFF];
+}
+
+__device__ __forceinline__ uint8_t to_bcd(int v) { return (uint8_t)(v + (v / 10) * 6); }
+
+__global__ void __launch_bounds__(128)
+xa_frame_kernel(int n_streams, int sectors_per_stream, int format, int sector_size, int file_number, int channel_number,
+                int coding, int lba, uint8_t *__restrict__ out, long out_stride) {
+	__shared__ uint32_t tab[256];
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+		uint32_t c = (uint32_t)i;
+		for (int b = 0; b < 8; b++) c = (c >> 1) ^ ((c & 1) ? 0xD8018001u : 0u);
+		tab[i] = c;
+	}
+	__syncthreads();
+	long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= (long)n_streams * sectors_per_stream) return;
+	int stream = (int)(id / sectors_per_stream), k = (int)(id - (long)stream * sectors_per_stream);
+	uint8_t *sec = out + (long)stream * out_stride + (long)k * sector_size - (2352 - sector_size);
+
+	uint8_t prior_coding = sec[19];
+	if (format == 1) {
+		int t = lba + k + 150;   // psx_cdrom_init_sector (cdrom.c:55-74)
+		sec[0] = 0;
+		for (int i = 1; i <= 10; i++) sec[i] = 0xFF;
+		sec[11] = 0;
+		sec[12] = to_bcd(t / 4500);
+		sec[13] = to_bcd((t / 75) % 60);
+		sec[14] = to_bcd(t % 75);
+		sec[15] = 2;
+		prior_coding = 0;
+	}
+	sec[16] = (uint8_t)file_number;
+	sec[17] = (uint8_t)(channel_number & 0x1F);
+	sec[18] = 0x04 | 0x20 | 0x40;                 // AUDIO | FORM2 | RT (adpcm.c:272-275)
+	sec[19] = (uint8_t)(prior_coding | coding);   // OR-ed in the 2336-byte format (adpcm.c:277-288)
+	for (int i = 0; i < 4; i++) sec[20 + i] = sec[16 + i];
+
+	uint32_t crc = 0;                             // cdrom.c:102-109: bytes 0x10 .. 0x92B
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(sec + 0x10);
+	for (int i = 0; i < 0x91C / 4; i++) {
+		uint32_t v = w[i];
+		crc = edc_step(crc, v & 0xFF, tab);
+		crc = edc_step(crc, (v >> 8) & 0xFF, tab);
+		crc = edc_step(crc, (v >> 16) & 0xFF, tab);
+		crc = edc_step(crc, v >> 24, tab);
+	}
+	*reinterpret_cast<uint32_t *>(sec + 0x92C) = crc;
+}
+
+// ---- launchers ---------------------------------------------------------------------------
+
+cudaError_t adpcm_launch_spu(int n_streams, const int16_t *d_samples, int pitch, long group_stride, int sample_count,
+                             const int *d_counts, void *d_states, uint8_t *d_out, long out_stride, cudaStream_t stream) {
+	if (n_streams <= 0) return cudaSuccess;
+	long threads = (long)n_streams * 16;
+	unsigned grid = (unsigned)((threads + ADPCM_THREADS - 1) / ADPCM_THREADS);
+	adpcm_spu_kernel<<<grid, ADPCM_THREADS, 0, stream>>>(n_streams, d_samples, pitch, group_stride, sample_count,
+	                                                     d_counts, static_cast<ChannelState *>(d_states), d_out,
+	                                                     out_stride);
+	return cudaGetLastError();
+}
+
+int adpcm_xa_sectors(int stereo, int bits_per_sample, int sample_count) {
+	int jump = bits_per_sample == 8 ? 112 : 224;
+	int total = stereo ? sample_count * 2 : sample_count;
+	return ((total + jump - 1) / jump + 17) / 18;
+}
+
+cudaError_t adpcm_launch_xa(int n_streams, int format, int stereo, int frequency, int bits_per_sample, int file_number,
+                            int channel_number, const int16_t *d_samples, long in_stride, int sample_count, int lba,
+                            void *d_states, uint8_t *d_out, long out_stride, bool frame_sectors, cudaStream_t stream) {
+	int sectors = adpcm_xa_sectors(stereo, bits_per_sample, sample_count);
+	if (n_streams <= 0 || sectors == 0) return cudaSuccess;
+	int sector_size = format == 0 ? 2336 : 2352;
+	constexpr int WARPS = ADPCM_THREADS / 32;
+	unsigned grid = (unsigned)((n_streams + WARPS - 1) / WARPS);
+	if (bits_per_sample == 8)
+		adpcm_xa_kernel<8><<<grid, ADPCM_THREADS, 0, stream>>>(n_streams, stereo, sector_size, d_samples, in_stride,
+		                                                       sample_count, static_cast<ChannelState *>(d_states),
+		                                                       d_out, out_stride);
+	else
+		adpcm_xa_kernel<4><<<grid, ADPCM_THREADS, 0, stream>>>(n_streams, stereo, sector_size, d_samples, in_stride,
+		                                                       sample_count, static_cast<ChannelState *>(d_states),
+		                                                       d_out, out_stride);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess || !frame_sectors) return e;
+	int coding = (stereo ? 1 : 0) | (frequency == 37800 ? 0 : 4) | (bits_per_sample == 8 ? 16 : 0);
+	long n = (long)n_streams * sectors;
+	xa_frame_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n_streams, sectors, format, sector_size, file_number,
+	                                                                  channel_number, coding, lba, d_out, out_stride);
+	return cudaGetLastError();
+}
+
+}  // namespace psxb200

@@ -1,0 +1,548 @@
+// MDEC "BS" v2/v3 frame encoder for sm_100a — the GPU side of encode_frame_bs
+// (reference psxavenc/mdec.c:580-755).
+//
+// Data flow for a batch of n NV21 frames resident in HBM:
+//
+//   bs_dct_kernel      one thread per 8x8 block: gathers the block from the NV21 frame
+//                      (mdec.c:605-634), level-shifts, runs the bit-exact integer FDCT in
+//                      registers (mdec.c:640) and stores |coef| (u16) in zig-zag order plus a
+//                      64-bit sign mask into a coefficient plane laid out so that the 32
+//                      lanes of a warp (32 consecutive blocks in bitstream order) read and
+//                      write 512 contiguous bytes per uint4 access.
+//   bs_pack_kernel     one CTA per frame, one thread per block and quant scale:
+//                      (1) first-fit quant-scale search q = 1,2,... (mdec.c:663-722): each
+//                          thread prices its blocks' run/level codes from a shared-memory
+//                          length LUT, the CTA sums and applies the byte-budget rule
+//                          8 + 2*ceil(bits/16) <= frame_max_size (flush_bits, mdec.c:321-333);
+//                      (2) exclusive scan of the per-block bit lengths in bitstream order;
+//                      (3) every thread re-quantises its blocks at the winning q and ORs its
+//                          codes into a shared-memory image of the bitstream at its bit
+//                          offset (encode_dct_block / encode_bits, mdec.c:441-510, 335-385);
+//                      (4) header (mdec.c:725-754) and coalesced copy-out with the 16-bit
+//                          little-endian word order of the format, zero padded.
+//
+// Division by the quantiser step uses an exact 32-bit reciprocal (DIVIDE_ROUNDED,
+// mdec.c:438, is round-half-away-from-zero == (|n| + d/2) / d in integers).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bs_encode.h"
+#include "bs_tables.h"
+#include "fdct.cuh"
+
+namespace psxb200 {
+
+// ---- constant tables -------------------------------------------------------------------
+// [q][i] -> (magic, half): level = umulhi(|coef| + half, magic), d = QUANT_ZZ[i] * q.
+__constant__ uint2 c_qparam[64 * 64];
+// [min(level,63)][run] -> code length in bits incl. sign (22 = escape), 0 for level 0.
+__constant__ uint8_t c_lenlut[64 * 64];
+// [run][level] -> code bits without the sign bit, 0 = escape.
+__constant__ uint16_t c_codelut[BS_AC_RUNS * BS_AC_LEVELS];
+// v3 DC delta codes: [0] chroma, [1] luma.
+__constant__ uint32_t c_dcvlc[2 * 512];
+
+__host__ __device__ constexpr int zigzag_at(int i) {
+	constexpr int t[64] = {BS_ZIGZAG_LIST};
+	return t[i];
+}
+
+void bs_upload_tables() {
+	static uint2 qparam[64 * 64];
+	static uint8_t lenlut[64 * 64];
+	static uint16_t codelut[BS_AC_RUNS * BS_AC_LEVELS];
+	static uint32_t dcvlc[2 * 512];
+	for (int q = 0; q < 64; q++) {
+		for (int i = 0; i < 64; i++) {
+			uint32_t d = (uint32_t)BS_QUANT_ZZ[i] * (q ? q : 1);
+			if (i == 0) d = 16;
+			qparam[q * 64 + i].x = (uint32_t)(0x100000000ull / d) + 1;
+			qparam[q * 64 + i].y = d / 2;
+		}
+	}
+	for (int lv = 0; lv < 64; lv++) {
+		for (int run = 0; run < 64; run++) {
+			int len = 0;
+			if (lv > 0) {
+				uint32_t e = (run < BS_AC_RUNS && lv < BS_AC_LEVELS) ? BS_AC_VLC[run * BS_AC_LEVELS + lv] : 0;
+				len = e ? (int)(e >> 24) : BS_AC_ESCAPE_BITS;
+			}
+			lenlut[(lv << 6) | run] = (uint8_t)len;
+		}
+	}
+	for (int i = 0; i < BS_AC_RUNS * BS_AC_LEVELS; i++)
+		codelut[i] = (uint16_t)((BS_AC_VLC[i] & 0xFFFFFF) >> 1);
+	for (int i = 0; i < 512; i++) {
+		dcvlc[i] = BS_DC_VLC_CHROMA[i];
+		dcvlc[512 + i] = BS_DC_VLC_LUMA[i];
+	}
+	cudaMemcpyToSymbol(c_qparam, qparam, sizeof(qparam));
+	cudaMemcpyToSymbol(c_lenlut, lenlut, sizeof(lenlut));
+	cudaMemcpyToSymbol(c_codelut, codelut, sizeof(codelut));
+	cudaMemcpyToSymbol(c_dcvlc, dcvlc, sizeof(dcvlc));
+}
+
+// ---- kernel 1: gather + FDCT -----------------------------------------------------------
+
+__device__ __forceinline__ int byte_of(uint32_t w, int k) { return (int)((w >> (8 * k)) & 0xFF); }
+
+template <int VARIANT>
+__global__ void __launch_bounds__(BS_DCT_THREADS)
+bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_frames, int width, int height,
+              int mbh, int nblk, int ngroups, uint4 *__restrict__ coefs, size_t frame_stride_u4) {
+	long gid = (long)blockIdx.x * BS_DCT_THREADS + threadIdx.x;
+	int lanes_per_frame = ngroups * 32;
+	int f = (int)(gid / lanes_per_frame);
+	if (f >= n_frames) return;
+	int b = (int)(gid - (long)f * lanes_per_frame);
+	if (b >= nblk) return;
+
+	// bitstream order: macroblock columns outermost, rows next, then Cr Cb Y1 Y2 Y3 Y4
+	int mb = b / 6, k = b - 6 * mb;
+	int mx = mb / mbh, my = mb - mx * mbh;
+	const uint8_t *fr = frames + (size_t)f * frame_bytes;
+
+	int v[64];
+	if (k < 2) {
+		// interleaved CrCb plane: Cr at even bytes, Cb at odd (mdec.c:627-628)
+		const uint8_t *p = fr + (size_t)width * height + (size_t)width * (my * 8) + mx * 16;
+#pragma unroll
+		for (int y = 0; y < 8; y++) {
+			uint4 r = __ldg(reinterpret_cast<const uint4 *>(p + (size_t)y * width));
+			uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+			for (int x = 0; x < 8; x++) {
+				uint32_t pair = w[x >> 1] >> (16 * (x & 1));
+				v[8 * y + x] = (int)((k ? (pair >> 8) : pair) & 0xFF) - 128;
+			}
+		}
+	} else {
+		int ox = ((k - 2) & 1) * 8, oy = ((k - 2) >> 1) * 8;
+		const uint8_t *p = fr + (size_t)width * (my * 16 + oy) + mx * 16 + ox;
+#pragma unroll
+		for (int y = 0; y < 8; y++) {
+			uint2 r = __ldg(reinterpret_cast<const uint2 *>(p + (size_t)y * width));
+#pragma unroll
+			for (int x = 0; x < 4; x++) {
+				v[8 * y + x] = byte_of(r.x, x) - 128;
+				v[8 * y + 4 + x] = byte_of(r.y, x) - 128;
+			}
+		}
+	}
+
+	fdct8x8<VARIANT>(v);
+
+	uint4 *dst = coefs + (size_t)f * frame_stride_u4 + (size_t)(b >> 5) * (BS_U4_PER_BLOCK * 32) + (b & 31);
+	uint32_t sign_lo = 0, sign_hi = 0;
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		uint32_t w[4];
+#pragma unroll
+		for (int t = 0; t < 4; t++) {
+			int i0 = 8 * j + 2 * t;
+			int c0 = v[zigzag_at(i0)], c1 = v[zigzag_at(i0 + 1)];
+			w[t] = (uint32_t)abs(c0) | ((uint32_t)abs(c1) << 16);
+			uint32_t s = ((uint32_t)c0 >> 31) | (((uint32_t)c1 >> 31) << 1);
+			if (i0 < 32) sign_lo |= s << i0; else sign_hi |= s << (i0 - 32);
+		}
+		dst[j * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+	}
+	dst[8 * 32] = make_uint4(sign_lo, sign_hi, 0, 0);
+}
+
+// ---- kernel 2: quant-scale search + bit packing ------------------------------------------
+
+struct PackSmem {
+	uint32_t *stream;   // bitstream image, 32-bit words, first stream bit = bit 31 of word 0
+	uint32_t *offs;     // per block: exclusive bit offset inside its group, then absolute
+	uint32_t *dcw;      // v3: per block DC code (len<<24 | code)
+	uint32_t *gtot;     // per group bit totals -> exclusive group bases
+	uint32_t *misc;     // [0..2] rotating frame totals, [3] nonzero AC count, [4..] scan scratch
+	uint16_t *lens;     // per block bit length at the current q
+	uint16_t *codelut;
+	int16_t *dcval;     // v3: per block quantised DC
+	uint8_t *lenlut;
+};
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+	return v;
+}
+
+// Loads the 8 magnitude words of block (group g, lane) into registers.
+__device__ __forceinline__ void load_mags(const uint4 *__restrict__ gp, uint32_t (&w)[32]) {
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		uint4 r = gp[j * 32];
+		w[4 * j + 0] = r.x; w[4 * j + 1] = r.y; w[4 * j + 2] = r.z; w[4 * j + 3] = r.w;
+	}
+}
+
+__device__ __forceinline__ uint32_t mag_at(const uint32_t (&w)[32], int i) {
+	return (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
+}
+
+// AC bit cost of one block at quant scale q (the pricing half of encode_dct_block).
+__device__ __forceinline__ int ac_bits(const uint32_t (&w)[32], int q, const uint8_t *lenlut) {
+	const uint2 *qp = c_qparam + q * 64;
+	int bits = 0, run = 0;
+#pragma unroll
+	for (int i = 1; i < 64; i++) {
+		uint2 p = qp[i];
+		uint32_t lv = __umulhi(mag_at(w, i) + p.y, p.x);
+		uint32_t m = min(lv, 63u);
+		bits += lenlut[(m << 6) | run];
+		run = lv ? 0 : run + 1;
+	}
+	return bits;
+}
+
+struct BitWriter {
+	uint32_t *words;
+	uint32_t cur;
+	int widx, fill;
+	__device__ __forceinline__ void begin(uint32_t *w, uint32_t bitpos) {
+		words = w; widx = (int)(bitpos >> 5); fill = (int)(bitpos & 31); cur = 0;
+	}
+	__device__ __forceinline__ void put(int len, uint32_t code) {
+		int room = 32 - fill;
+		if (len < room) {
+			cur |= code << (room - len);
+			fill += len;
+		} else {
+			int rem = len - room;
+			atomicOr(words + widx, cur | (code >> rem));
+			widx++;
+			cur = rem ? code << (32 - rem) : 0u;
+			fill = rem;
+		}
+	}
+	__device__ __forceinline__ void finish() {
+		if (fill) atomicOr(words + widx, cur);
+	}
+};
+
+// v3 DC prediction chain (mdec.c:455-461): last += 4*round((dc-last)/4) per plane. `last`
+// stays a multiple of 4, so with L = last/4, dc = 4a + r: L' = a + (r==3) for r != 2 and
+// L' = a + (L <= a) on exact ties. Each element is therefore a two-valued step function of
+// the incoming L; such functions compose in closed form, which turns the chain into a scan.
+struct DcFn { int t, lo, hi, valid; };
+__device__ __forceinline__ int dc_apply(const DcFn &f, int L) { return !f.valid ? L : (L <= f.t ? f.lo : f.hi); }
+__device__ __forceinline__ DcFn dc_then(const DcFn &f, const DcFn &g) {
+	if (!g.valid) return f;
+	if (!f.valid) return g;
+	return DcFn{f.t, dc_apply(g, f.lo), dc_apply(g, f.hi), 1};
+}
+__device__ __forceinline__ DcFn dc_elem(int dc) {
+	int a = dc >> 2, r = dc & 3;
+	if (r == 2) return DcFn{a, a + 1, a, 1};
+	int v = a + (r == 3);
+	return DcFn{0, v, v, 1};
+}
+__device__ __forceinline__ DcFn dc_shfl_up(const DcFn &f, int d) {
+	return DcFn{__shfl_up_sync(0xFFFFFFFFu, f.t, d), __shfl_up_sync(0xFFFFFFFFu, f.lo, d),
+	            __shfl_up_sync(0xFFFFFFFFu, f.hi, d), __shfl_up_sync(0xFFFFFFFFu, f.valid, d)};
+}
+
+// All threads of the CTA call this; fills dcw[] for every block of the frame.
+__device__ void dc_delta_codes(int codec, int nmb, const int16_t *dcval, uint32_t *dcw, int *scratch /* 4*32 ints */) {
+	const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
+	for (int plane = 0; plane < 3; plane++) {
+		int n = plane < 2 ? nmb : 4 * nmb;
+		int chunk = (n + T - 1) / T;
+		int lo = min(n, tid * chunk), hi = min(n, lo + chunk);
+		auto block_of = [&](int i) { return plane < 2 ? 6 * i + plane : 6 * (i >> 2) + 2 + (i & 3); };
+
+		DcFn acc{0, 0, 0, 0};
+		for (int i = lo; i < hi; i++) acc = dc_then(acc, dc_elem(dcval[block_of(i)]));
+
+		// inclusive scan across the CTA
+		DcFn inc = acc;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			DcFn up = dc_shfl_up(inc, d);
+			if (lane >= d) inc = dc_then(up, inc);
+		}
+		__syncthreads();
+		if (lane == 31) {
+			scratch[4 * wid + 0] = inc.t; scratch[4 * wid + 1] = inc.lo;
+			scratch[4 * wid + 2] = inc.hi; scratch[4 * wid + 3] = inc.valid;
+		}
+		__syncthreads();
+		DcFn pre{0, 0, 0, 0};   // everything before this warp
+		for (int w = 0; w < wid && w < nw; w++)
+			pre = dc_then(pre, DcFn{scratch[4 * w], scratch[4 * w + 1], scratch[4 * w + 2], scratch[4 * w + 3]});
+		DcFn excl = dc_shfl_up(inc, 1);
+		if (lane == 0) excl = DcFn{0, 0, 0, 0};
+		excl = dc_then(pre, excl);
+
+		int L = dc_apply(excl, 0);
+		const uint32_t *tab = c_dcvlc + (plane == 2 ? 512 : 0);
+		for (int i = lo; i < hi; i++) {
+			int b = block_of(i);
+			int Ln = dc_apply(dc_elem(dcval[b]), L);
+			int delta = Ln - L;
+			L = Ln;
+			if (codec == 2) {           // v3dc wrap-around (mdec.c:469-474)
+				if (delta < -0x80) delta += 0x100;
+				else if (delta > 0x80) delta -= 0x100;
+			}
+			dcw[b] = tab[delta & 0x1FF];
+		}
+	}
+	__syncthreads();
+}
+
+__device__ __forceinline__ int quant_dc(uint32_t mag, uint32_t negative) {
+	// round(c/16) half away from zero, clamp to [-512, 510] (mdec.c:447-449, 262-265)
+	int d = (int)((mag + 8) >> 4);
+	d = negative ? -d : d;
+	return max(-0x200, min(0x1FE, d));
+}
+
+template <bool V3, bool SMEM_STREAM>
+__global__ void __launch_bounds__(BS_PACK_MAX_THREADS)
+bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk, int ngroups, int nmb, int codec,
+               const int *__restrict__ max_sizes, int max_size_bound, uint8_t *__restrict__ out, size_t out_stride,
+               psxb200_bs_result_t *__restrict__ results, uint32_t *__restrict__ gstream, size_t gstream_stride) {
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+	const int f = blockIdx.x;
+	const int padded = ngroups * 32;
+	const int stream_words = (max_size_bound + 3) / 4 + 2;
+
+	PackSmem s;
+	{
+		uint8_t *p = smem_raw;
+		s.stream = reinterpret_cast<uint32_t *>(p); if (SMEM_STREAM) p += 4 * (size_t)stream_words;
+		s.offs = reinterpret_cast<uint32_t *>(p);   p += 4 * (size_t)padded;
+		s.dcw = reinterpret_cast<uint32_t *>(p);    if (V3) p += 4 * (size_t)padded;
+		s.gtot = reinterpret_cast<uint32_t *>(p);   p += 4 * (size_t)(ngroups + 1);
+		s.misc = reinterpret_cast<uint32_t *>(p);   p += 4 * (8 + 4 * 32);
+		s.lens = reinterpret_cast<uint16_t *>(p);   p += 2 * (size_t)padded;
+		s.codelut = reinterpret_cast<uint16_t *>(p); p += 2 * (BS_AC_RUNS * BS_AC_LEVELS);
+		s.dcval = reinterpret_cast<int16_t *>(p);   if (V3) p += 2 * (size_t)padded;
+		s.lenlut = p;
+	}
+	uint32_t *stream = SMEM_STREAM ? s.stream : gstream + (size_t)f * gstream_stride;
+
+	const uint4 *fc = coefs + (size_t)f * frame_stride_u4;
+	int max_size = max_sizes[f];
+	if (max_size > max_size_bound) max_size = 0;   // contract violation -> frame fails
+	const int words = max_size > 0 ? (max_size + 3) / 4 + 2 : 0;
+
+	for (int i = tid; i < 64 * 64 / 4; i += T)
+		reinterpret_cast<uint32_t *>(s.lenlut)[i] = reinterpret_cast<const uint32_t *>(c_lenlut)[i];
+	for (int i = tid; i < BS_AC_RUNS * BS_AC_LEVELS; i += T) s.codelut[i] = c_codelut[i];
+	for (int i = tid; i < words; i += T) stream[i] = 0;
+	if (tid < 8) s.misc[tid] = 0;
+	if (V3) {
+		for (int b = tid; b < nblk; b += T) {
+			const uint4 *gp = fc + (size_t)(b >> 5) * (BS_U4_PER_BLOCK * 32) + (b & 31);
+			uint32_t w0 = reinterpret_cast<const uint32_t *>(gp)[0];
+			uint32_t sg = reinterpret_cast<const uint32_t *>(gp + 8 * 32)[0];
+			s.dcval[b] = (int16_t)quant_dc(w0 & 0xFFFFu, sg & 1u);
+		}
+	}
+	__syncthreads();
+	if (V3) dc_delta_codes(codec, nmb, s.dcval, s.dcw, reinterpret_cast<int *>(s.misc + 8));
+
+	// ---- (1) first-fit quant scale search ------------------------------------------------
+	int q = 1;
+	uint32_t total_bits = 0;
+	for (; q < 64; q++) {
+		uint32_t mine = 0;
+		for (int g = wid; g < ngroups; g += nw) {
+			int b = g * 32 + lane;
+			int bits = 0;
+			if (b < nblk) {
+				uint32_t w[32];
+				load_mags(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane, w);
+				bits = ac_bits(w, q, s.lenlut) + 2 + (V3 ? (int)(s.dcw[b] >> 24) : 10);
+			}
+			s.lens[b] = (uint16_t)bits;
+			mine += bits;
+		}
+		mine = warp_sum(mine);
+		if (lane == 0) atomicAdd(&s.misc[q % 3], mine);
+		__syncthreads();
+		total_bits = s.misc[q % 3];
+		if (tid == 0) s.misc[(q + 2) % 3] = 0;
+		// stream = blocks + 10-bit end-of-frame code; byte budget rule of flush_bits
+		int units = (int)((total_bits + 10 + 15) >> 4);
+		if (8 + 2 * units <= max_size) break;
+	}
+
+	uint32_t *out32 = reinterpret_cast<uint32_t *>(out + (size_t)f * out_stride);
+	if (q >= 64) {
+		for (int i = tid; i < (max_size >> 2); i += T) out32[i] = 0;
+		for (int i = (max_size & ~3) + tid; i < max_size; i += T) out[(size_t)f * out_stride + i] = 0;
+		if (tid == 0) results[f] = psxb200_bs_result_t{0, 0, 64, 0};
+		return;
+	}
+
+	// ---- (2) exclusive scan of block bit lengths in bitstream order ---------------------
+	for (int g = wid; g < ngroups; g += nw) {
+		uint32_t v = s.lens[g * 32 + lane], inc = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+			if (lane >= d) inc += u;
+		}
+		s.offs[g * 32 + lane] = inc - v;
+		if (lane == 31) s.gtot[g] = inc;
+	}
+	__syncthreads();
+	if (wid == 0) {
+		uint32_t carry = 0;
+		for (int g0 = 0; g0 < ngroups; g0 += 32) {
+			int g = g0 + lane;
+			uint32_t v = g < ngroups ? s.gtot[g] : 0, inc = v;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+				if (lane >= d) inc += u;
+			}
+			if (g < ngroups) s.gtot[g] = carry + inc - v;
+			carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+		}
+	}
+	__syncthreads();
+
+	// ---- (3) emit --------------------------------------------------------------------------
+	{
+		const uint2 *qp = c_qparam + q * 64;
+		uint32_t nnz = 0;
+		for (int g = wid; g < ngroups; g += nw) {
+			int b = g * 32 + lane;
+			if (b >= nblk) continue;
+			const uint4 *gp = fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane;
+			uint32_t w[32];
+			load_mags(gp, w);
+			uint4 sg = gp[8 * 32];
+			BitWriter bw;
+			bw.begin(stream, s.gtot[g] + s.offs[b]);
+			if (V3) {
+				uint32_t e = s.dcw[b];
+				bw.put((int)(e >> 24), e & 0xFFFFFFu);
+			} else {
+				bw.put(10, (uint32_t)quant_dc(w[0] & 0xFFFFu, sg.x & 1u) & 0x3FFu);
+			}
+			int run = 0;
+#pragma unroll
+			for (int i = 1; i < 64; i++) {
+				uint2 p = qp[i];
+				uint32_t mag = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
+				uint32_t lv = __umulhi(mag + p.y, p.x);
+				if (lv) {
+					uint32_t neg = ((i < 32 ? sg.x : sg.y) >> (i & 31)) & 1u;
+					uint32_t c = (run < BS_AC_RUNS && lv < BS_AC_LEVELS) ? s.codelut[run * BS_AC_LEVELS + lv] : 0u;
+					if (c) {
+						bw.put(s.lenlut[(lv << 6) | run], (c << 1) | neg);
+					} else {
+						// clamp to [-512, 510] (mdec.c:262-265), 10-bit two's complement
+						int level = neg ? -(int)min(lv, 0x200u) : (int)min(lv, 0x1FEu);
+						bw.put(BS_AC_ESCAPE_BITS, (1u << 16) | ((uint32_t)run << 10) | ((uint32_t)level & 0x3FFu));
+					}
+					run = 0;
+					nnz++;
+				} else {
+					run++;
+				}
+			}
+			bw.put(2, 2u);   // end of block (mdec.c:502)
+			if (b == nblk - 1) bw.put(10, V3 ? 0x3FFu : 0x1FFu);   // end of frame (mdec.c:645-652, 710)
+			bw.finish();
+		}
+		nnz = warp_sum(nnz);
+		if (lane == 0) atomicAdd(&s.misc[3], nnz);
+	}
+	__syncthreads();
+
+	// ---- (4) header, results, copy-out -----------------------------------------------------
+	int units = (int)((total_bits + 10 + 15) >> 4);
+	int hwords = ((int)s.misc[3] + 2 * nblk + 2 + 0x3F) & ~0x3F;   // mdec.c:497,507,719,726
+	int blocks_used = (hwords + 1) >> 1;
+	if (tid == 0)
+		results[f] = psxb200_bs_result_t{(8 + 2 * units + 3) & ~3, blocks_used, q, hwords};
+	uint32_t hdr0 = (uint32_t)(blocks_used & 0xFFFF) | 0x38000000u;
+	uint32_t hdr1 = (uint32_t)q | ((V3 ? 3u : 2u) << 16);
+	for (int i = tid; i < (max_size >> 2); i += T) {
+		uint32_t v;
+		if (i == 0) v = hdr0;
+		else if (i == 1) v = hdr1;
+		else { uint32_t x = stream[i - 2]; v = (x >> 16) | (x << 16); }
+		out32[i] = v;
+	}
+	if (tid < (max_size & 3)) {
+		int i = (max_size & ~3) + tid;   // >= 8 here, since the frame fitted
+		uint32_t x = stream[(i >> 2) - 2];
+		uint32_t v = (x >> 16) | (x << 16);
+		out[(size_t)f * out_stride + i] = (uint8_t)(v >> (8 * (i & 3)));
+	}
+}
+
+// ---- launchers ---------------------------------------------------------------------------
+
+size_t bs_pack_smem_bytes(bool v3, bool smem_stream, int ngroups, int max_size_bound) {
+	size_t padded = (size_t)ngroups * 32;
+	size_t n = 0;
+	if (smem_stream) n += 4 * (size_t)((max_size_bound + 3) / 4 + 2);
+	n += 4 * padded;                     // offs
+	if (v3) n += 4 * padded;             // dcw
+	n += 4 * (size_t)(ngroups + 1);      // gtot
+	n += 4 * (8 + 4 * 32);               // misc
+	n += 2 * padded;                     // lens
+	n += 2 * (BS_AC_RUNS * BS_AC_LEVELS);
+	if (v3) n += 2 * padded;             // dcval
+	n += 64 * 64;                        // lenlut
+	return (n + 15) & ~(size_t)15;
+}
+
+cudaError_t bs_launch_dct(int fdct_variant, const uint8_t *d_frames, size_t frame_bytes, int n, int width, int height,
+                          const BsGeometry &geo, uint4 *d_coefs, cudaStream_t stream) {
+	long lanes = (long)n * geo.ngroups * 32;
+	unsigned grid = (unsigned)((lanes + BS_DCT_THREADS - 1) / BS_DCT_THREADS);
+	if (fdct_variant == FDCT_SSE2)
+		bs_dct_kernel<FDCT_SSE2><<<grid, BS_DCT_THREADS, 0, stream>>>(d_frames, frame_bytes, n, width, height, geo.mbh,
+		                                                              geo.nblk, geo.ngroups, d_coefs, geo.frame_stride_u4);
+	else
+		bs_dct_kernel<FDCT_ISLOW><<<grid, BS_DCT_THREADS, 0, stream>>>(d_frames, frame_bytes, n, width, height, geo.mbh,
+		                                                               geo.nblk, geo.ngroups, d_coefs, geo.frame_stride_u4);
+	return cudaGetLastError();
+}
+
+template <bool V3, bool SMEM_STREAM>
+static cudaError_t launch_pack_t(int threads, size_t smem, int n, const uint4 *d_coefs, const BsGeometry &geo, int codec,
+                                 const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
+                                 psxb200_bs_result_t *d_results, uint32_t *d_gstream, size_t gstream_stride,
+                                 cudaStream_t stream) {
+	auto kern = bs_pack_kernel<V3, SMEM_STREAM>;
+	static size_t configured = 0;
+	if (smem > configured) {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return e;
+		configured = smem;
+	}
+	kern<<<n, threads, smem, stream>>>(d_coefs, geo.frame_stride_u4, geo.nblk, geo.ngroups, geo.mbw * geo.mbh, codec,
+	                                   d_max_sizes, max_size_bound, d_out, out_stride, d_results, d_gstream,
+	                                   gstream_stride);
+	return cudaGetLastError();
+}
+
+cudaError_t bs_launch_pack(int codec, int threads, int n, const uint4 *d_coefs, const BsGeometry &geo,
+                           const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
+                           psxb200_bs_result_t *d_results, uint32_t *d_gstream, size_t gstream_stride,
+                           cudaStream_t stream) {
+	bool v3 = codec != 0;
+	bool smem_stream = d_gstream == nullptr;
+	size_t smem = bs_pack_smem_bytes(v3, smem_stream, geo.ngroups, max_size_bound);
+#define PSXB200_PACK_ARGS threads, smem, n, d_coefs, geo, codec, d_max_sizes, max_size_bound, d_out, out_stride, \
+	d_results, d_gstream, gstream_stride, stream
+	if (v3) return smem_stream ? launch_pack_t<true, true>(PSXB200_PACK_ARGS) : launch_pack_t<true, false>(PSXB200_PACK_ARGS);
+	return smem_stream ? launch_pack_t<false, true>(PSXB200_PACK_ARGS) : launch_pack_t<false, false>(PSXB200_PACK_ARGS);
+#undef PSXB200_PACK_ARGS
+}
+
+}  // namespace psxb200

@@ -133,6 +133,7 @@ def emit(path, prefix, guard):
     out.append("#define %sAC_ESCAPE_BITS 22\n" % prefix)
     out.append("/* raster index of the i-th zig-zag coefficient (mdec.c:213-222) */")
     out.append("static const uint8_t %sZIGZAG[64] = {\n%s\n};\n" % (prefix, fmt_array(zz, 8, "%2d")))
+    out.append("#define %sZIGZAG_LIST %s\n" % (prefix, ", ".join(str(z) for z in zz)))
     out.append("/* quantiser matrix, raster order (mdec.c:189-198) */")
     out.append("static const uint8_t %sQUANT[64] = {\n%s\n};\n" % (prefix, fmt_array(QUANT, 8, "%2d")))
     out.append("/* quantiser matrix in zig-zag order */")
