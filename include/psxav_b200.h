@@ -142,8 +142,9 @@ uint32_t psx_audio_spu_get_buffer_size(int sample_count);
 uint32_t psx_audio_xa_get_buffer_size_per_sector(psx_audio_xa_settings_t settings);
 uint32_t psx_audio_xa_get_samples_per_sector(psx_audio_xa_settings_t settings);
 uint32_t psx_audio_xa_get_sector_interleave(psx_audio_xa_settings_t settings);
-/* libpsxav/libpsxav.h:78-85 (adpcm.c:293). HOST pointers; the ADPCM search runs on the GPU,
- * sector framing / EDC on the host exactly as adpcm.c:262-332 + cdrom.c do. */
+/* libpsxav/libpsxav.h:78-85 (adpcm.c:293). HOST pointers; the ADPCM search, the sector
+ * framing (adpcm.c:262-332, cdrom.c:55-74) and the EDC (cdrom.c:30-41,102-109) all run on
+ * the GPU. Bytes the reference leaves untouched keep the caller's content. */
 int psx_audio_xa_encode(psx_audio_xa_settings_t settings, psx_audio_encoder_state_t *state,
                         const int16_t *samples, int sample_count, int lba, uint8_t *output);
 /* libpsxav/libpsxav.h:86-92 (adpcm.c:342) */
@@ -210,6 +211,13 @@ int psxb200_bs_encode_host(psxb200_bs_encoder_t *enc, int n, const uint8_t *h_fr
 
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 unsigned long long psxb200_launch_count(void);
+
+/* Optional per-kernel timing for benchmarks: while enabled, every internal launch pair
+ * (FDCT kernel, pack kernel) of psxb200_bs_encode_device is bracketed by CUDA events on the
+ * launching stream. psxb200_bs_timing_read waits for them, returns the summed durations in
+ * milliseconds and the number of launch pairs, and resets the counters. */
+void psxb200_bs_timing_enable(psxb200_bs_encoder_t *enc, int on);
+int psxb200_bs_timing_read(psxb200_bs_encoder_t *enc, double *dct_ms, double *pack_ms, int *launch_pairs);
 
 /* SPU-ADPCM, n_streams independent mono chains (adpcm.c:356-376 each).
  * Stream s reads sample i at d_samples[(s / pitch) * group_stride + (s % pitch) + i * pitch]

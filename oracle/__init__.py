@@ -17,6 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 RESTATED_SO = os.path.join(HERE, "liboracle.so")
 REFERENCE_SO = os.path.join(HERE, "_ref", "libpsxav_ref.so")
+DROPIN_DRIVER = os.path.join(HERE, "_ref", "dropin_driver")
 
 FDCT_ISLOW, FDCT_SSE2 = 0, 1
 CODEC_V2, CODEC_V3, CODEC_V3DC = 0, 1, 2
@@ -24,7 +25,7 @@ CODEC_V2, CODEC_V3, CODEC_V3DC = 0, 1, 2
 
 def build(force=False):
     """Compile liboracle.so and (when /root/reference is present) _ref/libpsxav_ref.so."""
-    args = ["make", "-C", HERE] + (["-B"] if force else [])
+    args = ["make", "-C", HERE] + (["-B"] if force else []) + ["all", "dropin"]
     subprocess.run(args, check=True, stdout=subprocess.DEVNULL)
 
 

@@ -85,6 +85,8 @@ SYMBOLS = {
     "psxb200_launch_count": (C.c_ulonglong, []),
     "psxb200_bs_create": (_P, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "psxb200_bs_destroy": (None, [_P]),
+    "psxb200_bs_timing_enable": (None, [_P, C.c_int]),
+    "psxb200_bs_timing_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "psxb200_bs_encode_device": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, C.c_size_t, _P, _P]),
     "psxb200_bs_encode_host": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "psxb200_spu_encode_device": (C.c_int, [C.c_int, _P, C.c_int, C.c_long, C.c_int, _P, _P, _P, C.c_long, _P]),
@@ -164,6 +166,16 @@ class BsEncoder:
             self.handle = None
 
     __del__ = close
+
+    def timing(self, on):
+        """Bracket every internal kernel launch with CUDA events (benchmarks only)."""
+        lib().psxb200_bs_timing_enable(self.handle, int(on))
+
+    def read_timing(self):
+        """-> (fdct kernel ms, pack kernel ms, launch pairs) since the last read."""
+        a, b, n = C.c_double(), C.c_double(), C.c_int()
+        _check(lib().psxb200_bs_timing_read(self.handle, C.byref(a), C.byref(b), C.byref(n)), "bs_timing_read")
+        return a.value, b.value, n.value
 
     def encode_device(self, n, d_frames, d_max_sizes, max_size_bound, d_out, out_stride, d_results, stream=None):
         """All pointers are device addresses (ints or torch tensors). Asynchronous on `stream`."""

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "psxav_b200.h"
 #include "adpcm_encode.h"
@@ -81,6 +82,19 @@ struct psxb200_bs_encoder {
 	DeviceBuffer<uint8_t> in[2], out[2];
 	DeviceBuffer<int> sizes[2];
 	DeviceBuffer<psxb200_bs_result_t> res[2];
+	// optional per-kernel timing (psxb200_bs_timing_*): three events per internal launch pair
+	bool timing = false;
+	std::vector<cudaEvent_t> events;
+	size_t events_used = 0;
+	cudaError_t mark(cudaStream_t st) {
+		if (events_used == events.size()) {
+			cudaEvent_t e;
+			cudaError_t rc = cudaEventCreate(&e);
+			if (rc != cudaSuccess) return rc;
+			events.push_back(e);
+		}
+		return cudaEventRecord(events[events_used++], st);
+	}
 
 	psxb200_bs_encoder(int c, int w, int h, int f, int mb)
 		: codec(c), width(w), height(h), fdct(f), max_batch(mb), pack_threads(320),
@@ -156,6 +170,7 @@ extern "C" void psxb200_bs_destroy(psxb200_bs_encoder_t *enc) {
 		enc->res[i].release();
 	}
 	enc->gstream.release();
+	for (cudaEvent_t e : enc->events) cudaEventDestroy(e);
 	delete enc;
 }
 
@@ -171,13 +186,40 @@ static int bs_encode_chunked(psxb200_bs_encoder *enc, uint4 *d_coefs, int n, con
 	}
 	for (int first = 0; first < n; first += enc->max_batch) {
 		int m = std::min(enc->max_batch, n - first);
+		if (enc->timing) CU_TRY(enc->mark(stream));
 		CU_TRY(bs_launch_dct(enc->fdct, d_frames + (size_t)first * enc->frame_bytes, enc->frame_bytes, m, enc->width,
 		                     enc->height, enc->geo, d_coefs, stream));
+		if (enc->timing) CU_TRY(enc->mark(stream));
 		CU_TRY(bs_launch_pack(enc->codec, enc->pack_threads, m, d_coefs, enc->geo, d_max_sizes + first, max_size_bound,
 		                      d_out + (size_t)first * out_stride, out_stride, d_results + first, gstream, gstride,
 		                      stream));
+		if (enc->timing) CU_TRY(enc->mark(stream));
 		g_launches += 2;
 	}
+	return 0;
+}
+
+extern "C" void psxb200_bs_timing_enable(psxb200_bs_encoder_t *enc, int on) {
+	enc->timing = on != 0;
+	enc->events_used = 0;
+}
+
+extern "C" int psxb200_bs_timing_read(psxb200_bs_encoder_t *enc, double *dct_ms, double *pack_ms, int *launch_pairs) {
+	double dct = 0, pack = 0;
+	int pairs = 0;
+	for (size_t i = 0; i + 3 <= enc->events_used; i += 3) {
+		float a = 0, b = 0;
+		CU_TRY(cudaEventSynchronize(enc->events[i + 2]));
+		CU_TRY(cudaEventElapsedTime(&a, enc->events[i], enc->events[i + 1]));
+		CU_TRY(cudaEventElapsedTime(&b, enc->events[i + 1], enc->events[i + 2]));
+		dct += a;
+		pack += b;
+		pairs++;
+	}
+	enc->events_used = 0;
+	*dct_ms = dct;
+	*pack_ms = pack;
+	*launch_pairs = pairs;
 	return 0;
 }
 
