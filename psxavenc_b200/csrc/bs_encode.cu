@@ -37,8 +37,9 @@ namespace psxb200 {
 __constant__ uint2 c_qparam[64 * 64];
 // [min(level,63)][run] -> code length in bits incl. sign (22 = escape), 0 for level 0.
 __constant__ uint8_t c_lenlut[64 * 64];
-// [run][level] -> code bits without the sign bit, 0 = escape.
-__constant__ uint16_t c_codelut[BS_AC_RUNS * BS_AC_LEVELS];
+// [min(level,63)][run] -> (len << 24) | code with the sign bit (LSB) clear; level 0 -> 0;
+// escape -> (22 << 24) with code 0. Copied to shared memory by every CTA.
+__device__ uint32_t g_vlc[64 * 64];
 // v3 DC delta codes: [0] chroma, [1] luma.
 __constant__ uint32_t c_dcvlc[2 * 512];
 
@@ -50,7 +51,7 @@ __host__ __device__ constexpr int zigzag_at(int i) {
 void bs_upload_tables() {
 	static uint2 qparam[64 * 64];
 	static uint8_t lenlut[64 * 64];
-	static uint16_t codelut[BS_AC_RUNS * BS_AC_LEVELS];
+	static uint32_t vlc[64 * 64];
 	static uint32_t dcvlc[2 * 512];
 	for (int q = 0; q < 64; q++) {
 		for (int i = 0; i < 64; i++) {
@@ -68,17 +69,17 @@ void bs_upload_tables() {
 				len = e ? (int)(e >> 24) : BS_AC_ESCAPE_BITS;
 			}
 			lenlut[(lv << 6) | run] = (uint8_t)len;
+			uint32_t e = (lv > 0 && run < BS_AC_RUNS && lv < BS_AC_LEVELS) ? BS_AC_VLC[run * BS_AC_LEVELS + lv] : 0;
+			vlc[(lv << 6) | run] = lv == 0 ? 0u : (e ? e : (uint32_t)BS_AC_ESCAPE_BITS << 24);
 		}
 	}
-	for (int i = 0; i < BS_AC_RUNS * BS_AC_LEVELS; i++)
-		codelut[i] = (uint16_t)((BS_AC_VLC[i] & 0xFFFFFF) >> 1);
 	for (int i = 0; i < 512; i++) {
 		dcvlc[i] = BS_DC_VLC_CHROMA[i];
 		dcvlc[512 + i] = BS_DC_VLC_LUMA[i];
 	}
 	cudaMemcpyToSymbol(c_qparam, qparam, sizeof(qparam));
 	cudaMemcpyToSymbol(c_lenlut, lenlut, sizeof(lenlut));
-	cudaMemcpyToSymbol(c_codelut, codelut, sizeof(codelut));
+	cudaMemcpyToSymbol(g_vlc, vlc, sizeof(vlc));
 	cudaMemcpyToSymbol(c_dcvlc, dcvlc, sizeof(dcvlc));
 }
 
@@ -158,10 +159,11 @@ struct PackSmem {
 	uint32_t *dcw;      // v3: per block DC code (len<<24 | code)
 	uint32_t *gtot;     // per group bit totals -> exclusive group bases
 	uint32_t *misc;     // [0..2] rotating frame totals, [3] nonzero AC count, [4..] scan scratch
+	uint32_t *vlc;      // [min(level,63)][run] -> (len<<24)|code, see g_vlc
 	uint16_t *lens;     // per block bit length at the current q
-	uint16_t *codelut;
 	int16_t *dcval;     // v3: per block quantised DC
 	uint8_t *lenlut;
+	uint8_t *lev;       // emit: min(level,63) of the thread's current block, [coef][thread] with stride lev_stride
 };
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
@@ -170,56 +172,83 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 	return v;
 }
 
-// Loads the 8 magnitude words of block (group g, lane) into registers.
-__device__ __forceinline__ void load_mags(const uint4 *__restrict__ gp, uint32_t (&w)[32]) {
+// Loads magnitude rows [4*HALF, 4*HALF+4) of block (group, lane): coefficients 32*HALF..32*HALF+31.
+template <int HALF>
+__device__ __forceinline__ void load_mags(const uint4 *__restrict__ gp, uint32_t (&w)[16]) {
 #pragma unroll
-	for (int j = 0; j < 8; j++) {
-		uint4 r = gp[j * 32];
+	for (int j = 0; j < 4; j++) {
+		uint4 r = gp[(4 * HALF + j) * 32];
 		w[4 * j + 0] = r.x; w[4 * j + 1] = r.y; w[4 * j + 2] = r.z; w[4 * j + 3] = r.w;
 	}
 }
 
-__device__ __forceinline__ uint32_t mag_at(const uint32_t (&w)[32], int i) {
+// |coef| number i (0..31) of the loaded half
+__device__ __forceinline__ uint32_t mag_at(const uint32_t (&w)[16], int i) {
 	return (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
 }
 
-// AC bit cost of one block at quant scale q (the pricing half of encode_dct_block).
-__device__ __forceinline__ int ac_bits(const uint32_t (&w)[32], int q, const uint8_t *lenlut) {
-	const uint2 *qp = c_qparam + q * 64;
-	int bits = 0, run = 0;
+// AC bit cost of one block at quant scale q (the pricing half of encode_dct_block), half a
+// block (32 coefficients) at a time to keep the register footprint small.
+template <int HALF>
+__device__ __forceinline__ void ac_bits_half(const uint32_t (&w)[16], int q, const uint8_t *lenlut, int &bits, int &run) {
+	const uint2 *qp = c_qparam + q * 64 + 32 * HALF;
 #pragma unroll
-	for (int i = 1; i < 64; i++) {
+	for (int i = (HALF ? 0 : 1); i < 32; i++) {
 		uint2 p = qp[i];
 		uint32_t lv = __umulhi(mag_at(w, i) + p.y, p.x);
 		uint32_t m = min(lv, 63u);
 		bits += lenlut[(m << 6) | run];
 		run = lv ? 0 : run + 1;
 	}
+}
+
+__device__ __forceinline__ int ac_bits(const uint4 *__restrict__ gp, int q, const uint8_t *lenlut) {
+	int bits = 0, run = 0;
+	uint32_t w[16];
+	load_mags<0>(gp, w);
+	ac_bits_half<0>(w, q, lenlut, bits, run);
+	load_mags<1>(gp, w);
+	ac_bits_half<1>(w, q, lenlut, bits, run);
 	return bits;
 }
 
+// Emit, convergent half: quantise 32 coefficients, park min(level,63) in the thread's column
+// of the level staging area and return the nonzero mask of the half.
+template <int HALF>
+__device__ __forceinline__ uint32_t stage_levels_half(const uint32_t (&w)[16], int q, uint8_t *lev, int lev_stride) {
+	const uint2 *qp = c_qparam + q * 64 + 32 * HALF;
+	uint32_t nz = 0;
+#pragma unroll
+	for (int i = (HALF ? 0 : 1); i < 32; i++) {
+		uint2 p = qp[i];
+		uint32_t m = min(__umulhi(mag_at(w, i) + p.y, p.x), 63u);
+		lev[(32 * HALF + i) * lev_stride] = (uint8_t)m;
+		nz += min(m, 1u) << i;
+	}
+	return nz;
+}
+
+// Appends MSB-first codes at an arbitrary bit position of the 32-bit-word stream image. Words
+// are shared with neighbouring blocks at both ends, hence the atomic OR on flush.
 struct BitWriter {
 	uint32_t *words;
-	uint32_t cur;
+	unsigned long long acc;   // pending bits, left-aligned; the top `fill` bits are valid
 	int widx, fill;
 	__device__ __forceinline__ void begin(uint32_t *w, uint32_t bitpos) {
-		words = w; widx = (int)(bitpos >> 5); fill = (int)(bitpos & 31); cur = 0;
+		words = w; widx = (int)(bitpos >> 5); fill = (int)(bitpos & 31); acc = 0;
 	}
-	__device__ __forceinline__ void put(int len, uint32_t code) {
-		int room = 32 - fill;
-		if (len < room) {
-			cur |= code << (room - len);
-			fill += len;
-		} else {
-			int rem = len - room;
-			atomicOr(words + widx, cur | (code >> rem));
+	__device__ __forceinline__ void put(int len, uint32_t code) {   // len <= 22, fill < 32 on entry
+		acc |= (unsigned long long)code << (64 - fill - len);
+		fill += len;
+		if (fill >= 32) {
+			atomicOr(words + widx, (uint32_t)(acc >> 32));
 			widx++;
-			cur = rem ? code << (32 - rem) : 0u;
-			fill = rem;
+			acc <<= 32;
+			fill -= 32;
 		}
 	}
 	__device__ __forceinline__ void finish() {
-		if (fill) atomicOr(words + widx, cur);
+		if (fill) atomicOr(words + widx, (uint32_t)(acc >> 32));
 	}
 };
 
@@ -301,8 +330,8 @@ __device__ __forceinline__ int quant_dc(uint32_t mag, uint32_t negative) {
 	return max(-0x200, min(0x1FE, d));
 }
 
-template <bool V3, bool SMEM_STREAM>
-__global__ void __launch_bounds__(BS_PACK_MAX_THREADS)
+template <bool V3, bool SMEM_STREAM, int MAX_THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS)
 bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk, int ngroups, int nmb, int codec,
                const int *__restrict__ max_sizes, int max_size_bound, uint8_t *__restrict__ out, size_t out_stride,
                psxb200_bs_result_t *__restrict__ results, uint32_t *__restrict__ gstream, size_t gstream_stride) {
@@ -320,11 +349,13 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		s.dcw = reinterpret_cast<uint32_t *>(p);    if (V3) p += 4 * (size_t)padded;
 		s.gtot = reinterpret_cast<uint32_t *>(p);   p += 4 * (size_t)(ngroups + 1);
 		s.misc = reinterpret_cast<uint32_t *>(p);   p += 4 * (8 + 4 * 32);
+		s.vlc = reinterpret_cast<uint32_t *>(p);    p += 4 * 64 * 64;
 		s.lens = reinterpret_cast<uint16_t *>(p);   p += 2 * (size_t)padded;
-		s.codelut = reinterpret_cast<uint16_t *>(p); p += 2 * (BS_AC_RUNS * BS_AC_LEVELS);
 		s.dcval = reinterpret_cast<int16_t *>(p);   if (V3) p += 2 * (size_t)padded;
-		s.lenlut = p;
+		s.lenlut = p;                               p += 64 * 64;
+		s.lev = p;
 	}
+	const int lev_stride = bs_lev_stride(T);
 	uint32_t *stream = SMEM_STREAM ? s.stream : gstream + (size_t)f * gstream_stride;
 
 	const uint4 *fc = coefs + (size_t)f * frame_stride_u4;
@@ -334,7 +365,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 
 	for (int i = tid; i < 64 * 64 / 4; i += T)
 		reinterpret_cast<uint32_t *>(s.lenlut)[i] = reinterpret_cast<const uint32_t *>(c_lenlut)[i];
-	for (int i = tid; i < BS_AC_RUNS * BS_AC_LEVELS; i += T) s.codelut[i] = c_codelut[i];
+	for (int i = tid; i < 64 * 64; i += T) s.vlc[i] = g_vlc[i];
 	for (int i = tid; i < words; i += T) stream[i] = 0;
 	if (tid < 8) s.misc[tid] = 0;
 	if (V3) {
@@ -357,9 +388,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 			int b = g * 32 + lane;
 			int bits = 0;
 			if (b < nblk) {
-				uint32_t w[32];
-				load_mags(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane, w);
-				bits = ac_bits(w, q, s.lenlut) + 2 + (V3 ? (int)(s.dcw[b] >> 24) : 10);
+				bits = ac_bits(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane, q, s.lenlut) + 2 + (V3 ? (int)(s.dcw[b] >> 24) : 10);
 			}
 			s.lens[b] = (uint16_t)bits;
 			mine += bits;
@@ -411,15 +440,23 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	__syncthreads();
 
 	// ---- (3) emit --------------------------------------------------------------------------
+	// Per block: a convergent pass re-quantises all 63 AC coefficients, parks min(level,63) in
+	// the thread's shared-memory column and builds a 64-bit nonzero mask; the codes are then
+	// produced by walking the set bits only (runs fall out of the bit positions).
 	{
 		const uint2 *qp = c_qparam + q * 64;
+		uint8_t *lev = s.lev + tid;
 		uint32_t nnz = 0;
 		for (int g = wid; g < ngroups; g += nw) {
 			int b = g * 32 + lane;
 			if (b >= nblk) continue;
 			const uint4 *gp = fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane;
-			uint32_t w[32];
-			load_mags(gp, w);
+			uint32_t w[16];
+			load_mags<0>(gp, w);
+			const uint32_t dc_mag = w[0] & 0xFFFFu;
+			uint32_t nz_lo = stage_levels_half<0>(w, q, lev, lev_stride);
+			load_mags<1>(gp, w);
+			uint32_t nz_hi = stage_levels_half<1>(w, q, lev, lev_stride);
 			uint4 sg = gp[8 * 32];
 			BitWriter bw;
 			bw.begin(stream, s.gtot[g] + s.offs[b]);
@@ -427,28 +464,31 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 				uint32_t e = s.dcw[b];
 				bw.put((int)(e >> 24), e & 0xFFFFFFu);
 			} else {
-				bw.put(10, (uint32_t)quant_dc(w[0] & 0xFFFFu, sg.x & 1u) & 0x3FFu);
+				bw.put(10, (uint32_t)quant_dc(dc_mag, sg.x & 1u) & 0x3FFu);
 			}
-			int run = 0;
-#pragma unroll
-			for (int i = 1; i < 64; i++) {
-				uint2 p = qp[i];
-				uint32_t mag = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
-				uint32_t lv = __umulhi(mag + p.y, p.x);
-				if (lv) {
-					uint32_t neg = ((i < 32 ? sg.x : sg.y) >> (i & 31)) & 1u;
-					uint32_t c = (run < BS_AC_RUNS && lv < BS_AC_LEVELS) ? s.codelut[run * BS_AC_LEVELS + lv] : 0u;
-					if (c) {
-						bw.put(s.lenlut[(lv << 6) | run], (c << 1) | neg);
-					} else {
-						// clamp to [-512, 510] (mdec.c:262-265), 10-bit two's complement
-						int level = neg ? -(int)min(lv, 0x200u) : (int)min(lv, 0x1FEu);
-						bw.put(BS_AC_ESCAPE_BITS, (1u << 16) | ((uint32_t)run << 10) | ((uint32_t)level & 0x3FFu));
-					}
-					run = 0;
-					nnz++;
+			unsigned long long nz = ((unsigned long long)nz_hi << 32) | nz_lo;
+			const unsigned long long signs = ((unsigned long long)sg.y << 32) | sg.x;
+			nnz += __popcll(nz);
+			int prev = 0;
+			while (nz) {
+				int i = __ffsll((long long)nz) - 1;
+				nz &= nz - 1;
+				int run = i - prev - 1;
+				prev = i;
+				uint32_t m = lev[i * lev_stride];
+				uint32_t neg = (uint32_t)(signs >> i) & 1u;
+				uint32_t e = s.vlc[(m << 6) | run];
+				if (e & 0xFFFFFFu) {
+					bw.put((int)(e >> 24), (e & 0xFFFFFFu) | neg);
 				} else {
-					run++;
+					// escape: exact level from the coefficient plane, clamped to [-512, 510]
+					// (mdec.c:262-265), as 10-bit two's complement
+					uint32_t word = reinterpret_cast<const uint32_t *>(gp + (i >> 3) * 32)[(i >> 1) & 3];
+					uint32_t mag = (i & 1) ? (word >> 16) : (word & 0xFFFFu);
+					uint2 pq = qp[i];
+					uint32_t lv = __umulhi(mag + pq.y, pq.x);
+					int level = neg ? -(int)min(lv, 0x200u) : (int)min(lv, 0x1FEu);
+					bw.put(BS_AC_ESCAPE_BITS, (1u << 16) | ((uint32_t)run << 10) | ((uint32_t)level & 0x3FFu));
 				}
 			}
 			bw.put(2, 2u);   // end of block (mdec.c:502)
@@ -485,7 +525,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 
 // ---- launchers ---------------------------------------------------------------------------
 
-size_t bs_pack_smem_bytes(bool v3, bool smem_stream, int ngroups, int max_size_bound) {
+size_t bs_pack_smem_bytes(bool v3, bool smem_stream, int ngroups, int max_size_bound, int threads) {
 	size_t padded = (size_t)ngroups * 32;
 	size_t n = 0;
 	if (smem_stream) n += 4 * (size_t)((max_size_bound + 3) / 4 + 2);
@@ -493,10 +533,11 @@ size_t bs_pack_smem_bytes(bool v3, bool smem_stream, int ngroups, int max_size_b
 	if (v3) n += 4 * padded;             // dcw
 	n += 4 * (size_t)(ngroups + 1);      // gtot
 	n += 4 * (8 + 4 * 32);               // misc
+	n += 4 * 64 * 64;                    // vlc
 	n += 2 * padded;                     // lens
-	n += 2 * (BS_AC_RUNS * BS_AC_LEVELS);
 	if (v3) n += 2 * padded;             // dcval
 	n += 64 * 64;                        // lenlut
+	n += 64 * (size_t)bs_lev_stride(threads);   // lev
 	return (n + 15) & ~(size_t)15;
 }
 
@@ -513,12 +554,12 @@ cudaError_t bs_launch_dct(int fdct_variant, const uint8_t *d_frames, size_t fram
 	return cudaGetLastError();
 }
 
-template <bool V3, bool SMEM_STREAM>
+template <bool V3, bool SMEM_STREAM, int MAX_THREADS, int MIN_CTAS>
 static cudaError_t launch_pack_t(int threads, size_t smem, int n, const uint4 *d_coefs, const BsGeometry &geo, int codec,
                                  const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
                                  psxb200_bs_result_t *d_results, uint32_t *d_gstream, size_t gstream_stride,
                                  cudaStream_t stream) {
-	auto kern = bs_pack_kernel<V3, SMEM_STREAM>;
+	auto kern = bs_pack_kernel<V3, SMEM_STREAM, MAX_THREADS, MIN_CTAS>;
 	static size_t configured = 0;
 	if (smem > configured) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -531,18 +572,39 @@ static cudaError_t launch_pack_t(int threads, size_t smem, int n, const uint4 *d
 	return cudaGetLastError();
 }
 
-cudaError_t bs_launch_pack(int codec, int threads, int n, const uint4 *d_coefs, const BsGeometry &geo,
+template <int MAX_THREADS, int MIN_CTAS>
+static cudaError_t launch_pack_cfg(bool v3, bool smem_stream, int threads, size_t smem, int n, const uint4 *d_coefs,
+                                   const BsGeometry &geo, int codec, const int *d_max_sizes, int max_size_bound,
+                                   uint8_t *d_out, size_t out_stride, psxb200_bs_result_t *d_results,
+                                   uint32_t *d_gstream, size_t gstream_stride, cudaStream_t stream) {
+#define PSXB200_PACK_ARGS threads, smem, n, d_coefs, geo, codec, d_max_sizes, max_size_bound, d_out, out_stride, \
+	d_results, d_gstream, gstream_stride, stream
+	if (v3)
+		return smem_stream ? launch_pack_t<true, true, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
+		                   : launch_pack_t<true, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
+	return smem_stream ? launch_pack_t<false, true, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
+	                   : launch_pack_t<false, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
+#undef PSXB200_PACK_ARGS
+}
+
+cudaError_t bs_launch_pack(int codec, int threads, int min_ctas, int n, const uint4 *d_coefs, const BsGeometry &geo,
                            const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
                            psxb200_bs_result_t *d_results, uint32_t *d_gstream, size_t gstream_stride,
                            cudaStream_t stream) {
 	bool v3 = codec != 0;
 	bool smem_stream = d_gstream == nullptr;
-	size_t smem = bs_pack_smem_bytes(v3, smem_stream, geo.ngroups, max_size_bound);
-#define PSXB200_PACK_ARGS threads, smem, n, d_coefs, geo, codec, d_max_sizes, max_size_bound, d_out, out_stride, \
-	d_results, d_gstream, gstream_stride, stream
-	if (v3) return smem_stream ? launch_pack_t<true, true>(PSXB200_PACK_ARGS) : launch_pack_t<true, false>(PSXB200_PACK_ARGS);
-	return smem_stream ? launch_pack_t<false, true>(PSXB200_PACK_ARGS) : launch_pack_t<false, false>(PSXB200_PACK_ARGS);
-#undef PSXB200_PACK_ARGS
+	size_t smem = bs_pack_smem_bytes(v3, smem_stream, geo.ngroups, max_size_bound, threads);
+#define PSXB200_CFG_ARGS v3, smem_stream, threads, smem, n, d_coefs, geo, codec, d_max_sizes, max_size_bound, d_out, \
+	out_stride, d_results, d_gstream, gstream_stride, stream
+	// register budget variants: (max threads per CTA, CTAs per SM the register file must hold)
+	if (threads <= 320) {
+		if (min_ctas >= 4) return launch_pack_cfg<320, 4>(PSXB200_CFG_ARGS);
+		if (min_ctas == 3) return launch_pack_cfg<320, 3>(PSXB200_CFG_ARGS);
+		return launch_pack_cfg<320, 2>(PSXB200_CFG_ARGS);
+	}
+	if (min_ctas >= 2) return launch_pack_cfg<BS_PACK_MAX_THREADS, 2>(PSXB200_CFG_ARGS);
+	return launch_pack_cfg<BS_PACK_MAX_THREADS, 1>(PSXB200_CFG_ARGS);
+#undef PSXB200_CFG_ARGS
 }
 
 }  // namespace psxb200

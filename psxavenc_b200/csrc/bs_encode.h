@@ -14,8 +14,9 @@ constexpr int BS_PACK_MAX_THREADS = 640;
 // per block in the coefficient plane: 8 uint4 of |coef| (u16 pairs, zig-zag order) + 1 uint4
 // holding the 64-bit sign mask
 constexpr int BS_U4_PER_BLOCK = 9;
-// bitstream images above this size are built in global memory instead of shared memory
-constexpr int BS_SMEM_STREAM_LIMIT = 96 * 1024;
+// the bitstream image lives in shared memory while the CTA's total stays below this, else in
+// global memory
+constexpr size_t BS_SMEM_BUDGET = 200 * 1024;
 
 struct BsGeometry {
 	int mbw, mbh;            // macroblocks per row / column
@@ -30,13 +31,20 @@ struct BsGeometry {
 };
 
 void bs_upload_tables();
-size_t bs_pack_smem_bytes(bool v3, bool smem_stream, int ngroups, int max_size_bound);
+size_t bs_pack_smem_bytes(bool v3, bool smem_stream, int ngroups, int max_size_bound, int threads);
+
+// Row stride (bytes) of the per-thread level staging columns: threads rounded so that the
+// stride in 32-bit words is odd, which spreads a warp's scattered byte reads over the banks.
+__host__ __device__ inline int bs_lev_stride(int threads) {
+	int s = (threads + 3) & ~3;
+	return ((s >> 2) & 1) ? s : s + 4;
+}
 
 cudaError_t bs_launch_dct(int fdct_variant, const uint8_t *d_frames, size_t frame_bytes, int n, int width, int height,
                           const BsGeometry &geo, uint4 *d_coefs, cudaStream_t stream);
 
-// d_gstream == nullptr: bitstream image in shared memory (max_size_bound <= BS_SMEM_STREAM_LIMIT)
-cudaError_t bs_launch_pack(int codec, int threads, int n, const uint4 *d_coefs, const BsGeometry &geo,
+// d_gstream == nullptr: bitstream image in shared memory (bs_pack_smem_bytes(.., true, ..) <= BS_SMEM_BUDGET)
+cudaError_t bs_launch_pack(int codec, int threads, int min_ctas, int n, const uint4 *d_coefs, const BsGeometry &geo,
                            const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
                            psxb200_bs_result_t *d_results, uint32_t *d_gstream, size_t gstream_stride,
                            cudaStream_t stream);

@@ -71,7 +71,7 @@ size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // ======================================================================================
 
 struct psxb200_bs_encoder {
-	int codec, width, height, fdct, max_batch, pack_threads;
+	int codec, width, height, fdct, max_batch, pack_threads, pack_min_ctas = 2;
 	size_t frame_bytes;
 	BsGeometry geo;
 	// coefficient planes: [0] serves the device API and host slot 0, [1] host slot 1
@@ -106,7 +106,7 @@ static int bs_pick_threads(const BsGeometry &geo) {
 	const char *env = getenv("PSXB200_PACK_THREADS");
 	if (env && atoi(env) >= 32) return std::min(BS_PACK_MAX_THREADS, atoi(env) / 32 * 32);
 	int best = 10, best_waste = 1 << 30;
-	for (int warps = 8; warps <= 16; warps++) {
+	for (int warps = 8; warps <= BS_PACK_MAX_THREADS / 32; warps++) {
 		int rounds = (geo.ngroups + warps - 1) / warps;
 		int waste = rounds * warps - geo.ngroups;
 		if (waste * best < best_waste * warps) {   // compare waste fractions
@@ -145,6 +145,7 @@ extern "C" psxb200_bs_encoder_t *psxb200_bs_create(int codec, int width, int hei
 	}
 	auto *enc = new psxb200_bs_encoder(codec, width, height, fdct_variant, max_batch);
 	enc->pack_threads = bs_pick_threads(enc->geo);
+	if (const char *env = getenv("PSXB200_PACK_MIN_CTAS")) enc->pack_min_ctas = atoi(env);
 	bs_upload_tables();
 	cudaError_t e = enc->coefs[0].reserve((size_t)max_batch * enc->geo.frame_stride_u4);
 	if (e == cudaSuccess) e = cudaGetLastError();
@@ -179,7 +180,7 @@ static int bs_encode_chunked(psxb200_bs_encoder *enc, uint4 *d_coefs, int n, con
                              psxb200_bs_result_t *d_results, cudaStream_t stream) {
 	uint32_t *gstream = nullptr;
 	size_t gstride = 0;
-	if (max_size_bound > BS_SMEM_STREAM_LIMIT) {
+	if (bs_pack_smem_bytes(enc->codec != 0, true, enc->geo.ngroups, max_size_bound, enc->pack_threads) > BS_SMEM_BUDGET) {
 		gstride = (size_t)(max_size_bound + 3) / 4 + 2;
 		CU_TRY(enc->gstream.reserve(gstride * enc->max_batch));
 		gstream = enc->gstream.ptr;
@@ -190,7 +191,7 @@ static int bs_encode_chunked(psxb200_bs_encoder *enc, uint4 *d_coefs, int n, con
 		CU_TRY(bs_launch_dct(enc->fdct, d_frames + (size_t)first * enc->frame_bytes, enc->frame_bytes, m, enc->width,
 		                     enc->height, enc->geo, d_coefs, stream));
 		if (enc->timing) CU_TRY(enc->mark(stream));
-		CU_TRY(bs_launch_pack(enc->codec, enc->pack_threads, m, d_coefs, enc->geo, d_max_sizes + first, max_size_bound,
+		CU_TRY(bs_launch_pack(enc->codec, enc->pack_threads, enc->pack_min_ctas, m, d_coefs, enc->geo, d_max_sizes + first, max_size_bound,
 		                      d_out + (size_t)first * out_stride, out_stride, d_results + first, gstream, gstride,
 		                      stream));
 		if (enc->timing) CU_TRY(enc->mark(stream));
