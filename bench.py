@@ -438,8 +438,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fdct", default="sse2", choices=["sse2", "islow"],
                     help="which FFmpeg AVDCT.fdct both arms reproduce bit-exactly (sse2 = this box's libavcodec)")
-    ap.add_argument("--chunk", type=int, default=int(os.environ.get("PSXB200_CHUNK", "512")),
-                    help="frames per internal kernel launch")
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("PSXB200_CHUNK", str(FRAMES_PER_STEP))),
+                    help="frames per internal kernel launch (device-resident path)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

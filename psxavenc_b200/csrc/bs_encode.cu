@@ -187,29 +187,39 @@ __device__ __forceinline__ uint32_t mag_at(const uint32_t (&w)[16], int i) {
 	return (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
 }
 
+// Integer multiply-add pinned to the FMA pipe (IMAD). The pricing loop is bound by the ALU
+// pipe (adds, min/max, compares, shifts-and-adds) while the FMA pipe idles; routing the index,
+// run-length and accumulate arithmetic through IMAD balances the two.
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+	uint32_t d;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+
 // AC bit cost of one block at quant scale q (the pricing half of encode_dct_block), half a
 // block (32 coefficients) at a time to keep the register footprint small.
 template <int HALF>
-__device__ __forceinline__ void ac_bits_half(const uint32_t (&w)[16], int q, const uint8_t *lenlut, int &bits, int &run) {
+__device__ __forceinline__ void ac_bits_half(const uint32_t (&w)[16], int q, const uint8_t *lenlut, uint32_t &bits, uint32_t &run) {
 	const uint2 *qp = c_qparam + q * 64 + 32 * HALF;
 #pragma unroll
 	for (int i = (HALF ? 0 : 1); i < 32; i++) {
 		uint2 p = qp[i];
 		uint32_t lv = __umulhi(mag_at(w, i) + p.y, p.x);
 		uint32_t m = min(lv, 63u);
-		bits += lenlut[(m << 6) | run];
-		run = lv ? 0 : run + 1;
+		bits = imad(lenlut[imad(m, 64u, run)], 1u, bits);
+		uint32_t z = imad(lv, 1u, 0xFFFFFFFFu) >> 31;      // 1 when the level is zero (lv < 2^31)
+		run = imad(run, z, z);                              // (run + 1) * z
 	}
 }
 
 __device__ __forceinline__ int ac_bits(const uint4 *__restrict__ gp, int q, const uint8_t *lenlut) {
-	int bits = 0, run = 0;
+	uint32_t bits = 0, run = 0;
 	uint32_t w[16];
 	load_mags<0>(gp, w);
 	ac_bits_half<0>(w, q, lenlut, bits, run);
 	load_mags<1>(gp, w);
 	ac_bits_half<1>(w, q, lenlut, bits, run);
-	return bits;
+	return (int)bits;
 }
 
 // Emit, convergent half: quantise 32 coefficients, park min(level,63) in the thread's column
@@ -223,7 +233,7 @@ __device__ __forceinline__ uint32_t stage_levels_half(const uint32_t (&w)[16], i
 		uint2 p = qp[i];
 		uint32_t m = min(__umulhi(mag_at(w, i) + p.y, p.x), 63u);
 		lev[(32 * HALF + i) * lev_stride] = (uint8_t)m;
-		nz += min(m, 1u) << i;
+		nz = imad(min(m, 1u), 1u << i, nz);
 	}
 	return nz;
 }
@@ -341,18 +351,19 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	const int padded = ngroups * 32;
 	const int stream_words = (max_size_bound + 3) / 4 + 2;
 
+	// fixed-size tables first so that their shared-memory addresses are compile-time offsets
 	PackSmem s;
 	{
 		uint8_t *p = smem_raw;
+		s.lenlut = p;                               p += 64 * 64;
+		s.vlc = reinterpret_cast<uint32_t *>(p);    p += 4 * 64 * 64;
+		s.misc = reinterpret_cast<uint32_t *>(p);   p += 4 * (8 + 4 * 32);
 		s.stream = reinterpret_cast<uint32_t *>(p); if (SMEM_STREAM) p += 4 * (size_t)stream_words;
 		s.offs = reinterpret_cast<uint32_t *>(p);   p += 4 * (size_t)padded;
 		s.dcw = reinterpret_cast<uint32_t *>(p);    if (V3) p += 4 * (size_t)padded;
 		s.gtot = reinterpret_cast<uint32_t *>(p);   p += 4 * (size_t)(ngroups + 1);
-		s.misc = reinterpret_cast<uint32_t *>(p);   p += 4 * (8 + 4 * 32);
-		s.vlc = reinterpret_cast<uint32_t *>(p);    p += 4 * 64 * 64;
 		s.lens = reinterpret_cast<uint16_t *>(p);   p += 2 * (size_t)padded;
 		s.dcval = reinterpret_cast<int16_t *>(p);   if (V3) p += 2 * (size_t)padded;
-		s.lenlut = p;                               p += 64 * 64;
 		s.lev = p;
 	}
 	const int lev_stride = bs_lev_stride(T);

@@ -71,7 +71,7 @@ size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // ======================================================================================
 
 struct psxb200_bs_encoder {
-	int codec, width, height, fdct, max_batch, pack_threads, pack_min_ctas = 2;
+	int codec, width, height, fdct, max_batch, host_chunk, pack_threads, pack_min_ctas = 3;
 	size_t frame_bytes;
 	BsGeometry geo;
 	// coefficient planes: [0] serves the device API and host slot 0, [1] host slot 1
@@ -97,24 +97,17 @@ struct psxb200_bs_encoder {
 	}
 
 	psxb200_bs_encoder(int c, int w, int h, int f, int mb)
-		: codec(c), width(w), height(h), fdct(f), max_batch(mb), pack_threads(320),
+		: codec(c), width(w), height(h), fdct(f), max_batch(mb), host_chunk(mb < 512 ? mb : 512), pack_threads(320),
 		  frame_bytes((size_t)w * h * 3 / 2), geo(w, h) {}
 };
 
 static int bs_pick_threads(const BsGeometry &geo) {
-	// warps per CTA such that the groups of 32 blocks divide evenly with little tail waste
+	// 10 warps per CTA leave 64 registers per thread at 3 CTAs per SM (no spills) and divide the
+	// usual frame sizes' groups of 32 blocks with <= 5 % idle warp slots (320x240: 57 groups in
+	// 6 rounds, 640x480: 225 in 23); measured best on B200 (profiles/r1_sweeps.md).
 	const char *env = getenv("PSXB200_PACK_THREADS");
 	if (env && atoi(env) >= 32) return std::min(BS_PACK_MAX_THREADS, atoi(env) / 32 * 32);
-	int best = 10, best_waste = 1 << 30;
-	for (int warps = 8; warps <= BS_PACK_MAX_THREADS / 32; warps++) {
-		int rounds = (geo.ngroups + warps - 1) / warps;
-		int waste = rounds * warps - geo.ngroups;
-		if (waste * best < best_waste * warps) {   // compare waste fractions
-			best = warps;
-			best_waste = waste;
-		}
-	}
-	return best * 32;
+	return 32 * std::max(1, std::min(10, geo.ngroups));
 }
 
 extern "C" int psxb200_device_count(void) {
@@ -146,6 +139,7 @@ extern "C" psxb200_bs_encoder_t *psxb200_bs_create(int codec, int width, int hei
 	auto *enc = new psxb200_bs_encoder(codec, width, height, fdct_variant, max_batch);
 	enc->pack_threads = bs_pick_threads(enc->geo);
 	if (const char *env = getenv("PSXB200_PACK_MIN_CTAS")) enc->pack_min_ctas = atoi(env);
+	if (const char *env = getenv("PSXB200_HOST_CHUNK")) enc->host_chunk = std::max(1, std::min(max_batch, atoi(env)));
 	bs_upload_tables();
 	cudaError_t e = enc->coefs[0].reserve((size_t)max_batch * enc->geo.frame_stride_u4);
 	if (e == cudaSuccess) e = cudaGetLastError();
@@ -244,23 +238,26 @@ extern "C" int psxb200_bs_encode_host(psxb200_bs_encoder_t *enc, int n, const ui
 	for (int i = 0; i < 2; i++) {
 		if (!enc->streams[i]) CU_TRY(cudaStreamCreateWithFlags(&enc->streams[i], cudaStreamNonBlocking));
 	}
-	CU_TRY(enc->coefs[1].reserve((size_t)enc->max_batch * enc->geo.frame_stride_u4));
+	// chunks of host_chunk frames ping-pong between two streams: copy-in of one chunk overlaps
+	// the kernels and copy-out of the other
+	const int hc = enc->host_chunk;
+	CU_TRY(enc->coefs[1].reserve((size_t)hc * enc->geo.frame_stride_u4));
 
-	for (int first = 0, chunk = 0; first < n; first += enc->max_batch, chunk++) {
+	for (int first = 0, chunk = 0; first < n; first += hc, chunk++) {
 		int slot = chunk & 1;
-		int m = std::min(enc->max_batch, n - first);
+		int m = std::min(hc, n - first);
 		cudaStream_t st = enc->streams[slot];
 		int bound = 8;
 		for (int i = 0; i < m; i++) bound = std::max(bound, h_max_sizes[first + i]);
-		if ((size_t)bound > out_stride) return fail("psxb200_bs_encode_host: frame_max_size %d > out_stride", bound);
+		if ((size_t)bound > out_stride && n > 1) return fail("psxb200_bs_encode_host: frame_max_size %d > out_stride", bound);
 		size_t dstride = round_up((size_t)bound, 16);
 
 		// the slot's previous chunk has fully drained when its stream is idle
 		CU_TRY(cudaStreamSynchronize(st));
-		CU_TRY(enc->in[slot].reserve((size_t)enc->max_batch * enc->frame_bytes));
-		CU_TRY(enc->out[slot].reserve((size_t)enc->max_batch * dstride));
-		CU_TRY(enc->sizes[slot].reserve(enc->max_batch));
-		CU_TRY(enc->res[slot].reserve(enc->max_batch));
+		CU_TRY(enc->in[slot].reserve((size_t)hc * enc->frame_bytes));
+		CU_TRY(enc->out[slot].reserve((size_t)hc * dstride));
+		CU_TRY(enc->sizes[slot].reserve(hc));
+		CU_TRY(enc->res[slot].reserve(hc));
 
 		CU_TRY(cudaMemcpyAsync(enc->in[slot].ptr, h_frames + (size_t)first * enc->frame_bytes, (size_t)m * enc->frame_bytes,
 		                       cudaMemcpyHostToDevice, st));
@@ -268,8 +265,8 @@ extern "C" int psxb200_bs_encode_host(psxb200_bs_encoder_t *enc, int n, const ui
 		if (bs_encode_chunked(enc, enc->coefs[slot].ptr, m, enc->in[slot].ptr, enc->sizes[slot].ptr, bound,
 		                      enc->out[slot].ptr, dstride, enc->res[slot].ptr, st))
 			return -1;
-		CU_TRY(cudaMemcpy2DAsync(h_out + (size_t)first * out_stride, out_stride, enc->out[slot].ptr, dstride, (size_t)bound, m,
-		                         cudaMemcpyDeviceToHost, st));
+		CU_TRY(cudaMemcpy2DAsync(h_out + (size_t)first * out_stride, std::max(out_stride, (size_t)bound), enc->out[slot].ptr,
+		                         dstride, (size_t)bound, m, cudaMemcpyDeviceToHost, st));
 		CU_TRY(cudaMemcpyAsync(h_results + first, enc->res[slot].ptr, (size_t)m * sizeof(psxb200_bs_result_t),
 		                       cudaMemcpyDeviceToHost, st));
 	}
