@@ -114,7 +114,7 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
 #pragma unroll
 			for (int x = 0; x < 8; x++) {
 				uint32_t pair = w[x >> 1] >> (16 * (x & 1));
-				v[8 * y + x] = (int)((k ? (pair >> 8) : pair) & 0xFF) - 128;
+				v[8 * y + x] = (int)((k ? (pair >> 8) : pair) & 0xFF);
 			}
 		}
 	} else {
@@ -125,13 +125,17 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
 			uint2 r = __ldg(reinterpret_cast<const uint2 *>(p + (size_t)y * width));
 #pragma unroll
 			for (int x = 0; x < 4; x++) {
-				v[8 * y + x] = byte_of(r.x, x) - 128;
-				v[8 * y + 4 + x] = byte_of(r.y, x) - 128;
+				v[8 * y + x] = byte_of(r.x, x);
+				v[8 * y + 4 + x] = byte_of(r.y, x);
 			}
 		}
 	}
 
+	// The reference level-shifts every sample by -128 first (mdec.c:627-632). Both FDCT variants
+	// only ever take differences of samples except in the DC term, where the 64 offsets add up
+	// to exactly 8192 through both passes' exact scalings, so the shift is applied once here.
 	fdct8x8<VARIANT>(v);
+	v[0] -= 8192;
 
 	uint4 *dst = coefs + (size_t)f * frame_stride_u4 + (size_t)(b >> 5) * (BS_U4_PER_BLOCK * 32) + (b & 31);
 	uint32_t sign_lo = 0, sign_hi = 0;
@@ -155,13 +159,12 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
 
 struct PackSmem {
 	uint32_t *stream;   // bitstream image, 32-bit words, first stream bit = bit 31 of word 0
-	uint32_t *offs;     // per block: exclusive bit offset inside its group, then absolute
-	uint32_t *dcw;      // v3: per block DC code (len<<24 | code)
+	uint32_t *dctab;    // v3: DC delta codes, [0..511] chroma, [512..1023] luma (len<<24 | code)
 	uint32_t *gtot;     // per group bit totals -> exclusive group bases
 	uint32_t *misc;     // [0..2] rotating frame totals, [3] nonzero AC count, [4..] scan scratch
 	uint32_t *vlc;      // [min(level,63)][run] -> (len<<24)|code, see g_vlc
-	uint16_t *lens;     // per block bit length at the current q
-	int16_t *dcval;     // v3: per block quantised DC
+	uint16_t *lens;     // per block bit length at the current q; after the scan: exclusive offset in its group
+	int16_t *dcval;     // v3: per block quantised DC, replaced in place by its coded delta
 	uint8_t *lenlut;
 	uint8_t *lev;       // emit: min(level,63) of the thread's current block, [coef][thread] with stride lev_stride
 };
@@ -241,24 +244,27 @@ __device__ __forceinline__ uint32_t stage_levels_half(const uint32_t (&w)[16], i
 // Appends MSB-first codes at an arbitrary bit position of the 32-bit-word stream image. Words
 // are shared with neighbouring blocks at both ends, hence the atomic OR on flush.
 struct BitWriter {
-	uint32_t *words;
-	unsigned long long acc;   // pending bits, left-aligned; the top `fill` bits are valid
-	int widx, fill;
+	uint32_t *words;   // next word to flush
+	uint32_t cur;      // pending bits, left-aligned; the top `fill` bits are valid
+	int fill;
 	__device__ __forceinline__ void begin(uint32_t *w, uint32_t bitpos) {
-		words = w; widx = (int)(bitpos >> 5); fill = (int)(bitpos & 31); acc = 0;
+		words = w + (bitpos >> 5); fill = (int)(bitpos & 31); cur = 0;
 	}
-	__device__ __forceinline__ void put(int len, uint32_t code) {   // len <= 22, fill < 32 on entry
-		acc |= (unsigned long long)code << (64 - fill - len);
-		fill += len;
-		if (fill >= 32) {
-			atomicOr(words + widx, (uint32_t)(acc >> 32));
-			widx++;
-			acc <<= 32;
-			fill -= 32;
+	__device__ __forceinline__ void put(int len, uint32_t code) {   // 1 <= len <= 22, fill < 32 on entry
+		int room = 32 - fill;
+		if (len < room) {
+			cur |= code << (room - len);
+			fill += len;
+		} else {
+			int rem = len - room;
+			atomicOr(words, cur | (code >> rem));
+			words++;
+			cur = rem ? code << (32 - rem) : 0u;
+			fill = rem;
 		}
 	}
 	__device__ __forceinline__ void finish() {
-		if (fill) atomicOr(words + widx, (uint32_t)(acc >> 32));
+		if (fill) atomicOr(words, cur);
 	}
 };
 
@@ -284,8 +290,9 @@ __device__ __forceinline__ DcFn dc_shfl_up(const DcFn &f, int d) {
 	            __shfl_up_sync(0xFFFFFFFFu, f.hi, d), __shfl_up_sync(0xFFFFFFFFu, f.valid, d)};
 }
 
-// All threads of the CTA call this; fills dcw[] for every block of the frame.
-__device__ void dc_delta_codes(int codec, int nmb, const int16_t *dcval, uint32_t *dcw, int *scratch /* 4*32 ints */) {
+// All threads of the CTA call this; replaces dcval[] (quantised DC per block) by the delta
+// that gets coded, for every block of the frame.
+__device__ void dc_delta_codes(int codec, int nmb, int16_t *dcval, int *scratch /* 4*32 ints */) {
 	const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
 	for (int plane = 0; plane < 3; plane++) {
 		int n = plane < 2 ? nmb : 4 * nmb;
@@ -317,7 +324,6 @@ __device__ void dc_delta_codes(int codec, int nmb, const int16_t *dcval, uint32_
 		excl = dc_then(pre, excl);
 
 		int L = dc_apply(excl, 0);
-		const uint32_t *tab = c_dcvlc + (plane == 2 ? 512 : 0);
 		for (int i = lo; i < hi; i++) {
 			int b = block_of(i);
 			int Ln = dc_apply(dc_elem(dcval[b]), L);
@@ -327,7 +333,7 @@ __device__ void dc_delta_codes(int codec, int nmb, const int16_t *dcval, uint32_
 				if (delta < -0x80) delta += 0x100;
 				else if (delta > 0x80) delta -= 0x100;
 			}
-			dcw[b] = tab[delta & 0x1FF];
+			dcval[b] = (int16_t)delta;
 		}
 	}
 	__syncthreads();
@@ -359,8 +365,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		s.vlc = reinterpret_cast<uint32_t *>(p);    p += 4 * 64 * 64;
 		s.misc = reinterpret_cast<uint32_t *>(p);   p += 4 * (8 + 4 * 32);
 		s.stream = reinterpret_cast<uint32_t *>(p); if (SMEM_STREAM) p += 4 * (size_t)stream_words;
-		s.offs = reinterpret_cast<uint32_t *>(p);   p += 4 * (size_t)padded;
-		s.dcw = reinterpret_cast<uint32_t *>(p);    if (V3) p += 4 * (size_t)padded;
+		s.dctab = reinterpret_cast<uint32_t *>(p);  if (V3) p += 4 * 1024;
 		s.gtot = reinterpret_cast<uint32_t *>(p);   p += 4 * (size_t)(ngroups + 1);
 		s.lens = reinterpret_cast<uint16_t *>(p);   p += 2 * (size_t)padded;
 		s.dcval = reinterpret_cast<int16_t *>(p);   if (V3) p += 2 * (size_t)padded;
@@ -377,6 +382,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	for (int i = tid; i < 64 * 64 / 4; i += T)
 		reinterpret_cast<uint32_t *>(s.lenlut)[i] = reinterpret_cast<const uint32_t *>(c_lenlut)[i];
 	for (int i = tid; i < 64 * 64; i += T) s.vlc[i] = g_vlc[i];
+	if (V3) for (int i = tid; i < 1024; i += T) s.dctab[i] = c_dcvlc[i];
 	for (int i = tid; i < words; i += T) stream[i] = 0;
 	if (tid < 8) s.misc[tid] = 0;
 	if (V3) {
@@ -388,7 +394,9 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		}
 	}
 	__syncthreads();
-	if (V3) dc_delta_codes(codec, nmb, s.dcval, s.dcw, reinterpret_cast<int *>(s.misc + 8));
+	if (V3) dc_delta_codes(codec, nmb, s.dcval, reinterpret_cast<int *>(s.misc + 8));
+	// code of block b's DC delta (chroma table for Cr/Cb, luma for Y1..Y4)
+	auto dc_code = [&](int b) { return s.dctab[((b % 6) < 2 ? 0 : 512) + (s.dcval[b] & 0x1FF)]; };
 
 	// ---- (1) first-fit quant scale search ------------------------------------------------
 	int q = 1;
@@ -399,7 +407,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 			int b = g * 32 + lane;
 			int bits = 0;
 			if (b < nblk) {
-				bits = ac_bits(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane, q, s.lenlut) + 2 + (V3 ? (int)(s.dcw[b] >> 24) : 10);
+				bits = ac_bits(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane, q, s.lenlut) + 2 + (V3 ? (int)(dc_code(b) >> 24) : 10);
 			}
 			s.lens[b] = (uint16_t)bits;
 			mine += bits;
@@ -430,7 +438,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 			uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, d);
 			if (lane >= d) inc += u;
 		}
-		s.offs[g * 32 + lane] = inc - v;
+		s.lens[g * 32 + lane] = (uint16_t)(inc - v);
 		if (lane == 31) s.gtot[g] = inc;
 	}
 	__syncthreads();
@@ -470,36 +478,41 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 			uint32_t nz_hi = stage_levels_half<1>(w, q, lev, lev_stride);
 			uint4 sg = gp[8 * 32];
 			BitWriter bw;
-			bw.begin(stream, s.gtot[g] + s.offs[b]);
+			bw.begin(stream, s.gtot[g] + s.lens[b]);
 			if (V3) {
-				uint32_t e = s.dcw[b];
+				uint32_t e = dc_code(b);
 				bw.put((int)(e >> 24), e & 0xFFFFFFu);
 			} else {
 				bw.put(10, (uint32_t)quant_dc(dc_mag, sg.x & 1u) & 0x3FFu);
 			}
-			unsigned long long nz = ((unsigned long long)nz_hi << 32) | nz_lo;
-			const unsigned long long signs = ((unsigned long long)sg.y << 32) | sg.x;
-			nnz += __popcll(nz);
+			nnz += __popc(nz_lo) + __popc(nz_hi);
 			int prev = 0;
-			while (nz) {
-				int i = __ffsll((long long)nz) - 1;
-				nz &= nz - 1;
-				int run = i - prev - 1;
-				prev = i;
-				uint32_t m = lev[i * lev_stride];
-				uint32_t neg = (uint32_t)(signs >> i) & 1u;
-				uint32_t e = s.vlc[(m << 6) | run];
-				if (e & 0xFFFFFFu) {
-					bw.put((int)(e >> 24), (e & 0xFFFFFFu) | neg);
-				} else {
-					// escape: exact level from the coefficient plane, clamped to [-512, 510]
-					// (mdec.c:262-265), as 10-bit two's complement
-					uint32_t word = reinterpret_cast<const uint32_t *>(gp + (i >> 3) * 32)[(i >> 1) & 3];
-					uint32_t mag = (i & 1) ? (word >> 16) : (word & 0xFFFFu);
-					uint2 pq = qp[i];
-					uint32_t lv = __umulhi(mag + pq.y, pq.x);
-					int level = neg ? -(int)min(lv, 0x200u) : (int)min(lv, 0x1FEu);
-					bw.put(BS_AC_ESCAPE_BITS, (1u << 16) | ((uint32_t)run << 10) | ((uint32_t)level & 0x3FFu));
+#pragma unroll
+			for (int half = 0; half < 2; half++) {
+				uint32_t nz = half ? nz_hi : nz_lo;
+				const uint32_t signs = half ? sg.y : sg.x;
+				const uint8_t *lv = lev + 32 * half * lev_stride;
+				while (nz) {
+					int i = __ffs((int)nz) - 1;
+					nz &= nz - 1;
+					int pos = 32 * half + i;
+					int run = pos - prev - 1;
+					prev = pos;
+					uint32_t m = lv[i * lev_stride];
+					uint32_t neg = (signs >> i) & 1u;
+					uint32_t e = s.vlc[(m << 6) | run];
+					if (e & 0xFFFFFFu) {
+						bw.put((int)(e >> 24), (e & 0xFFFFFFu) | neg);
+					} else {
+						// escape: exact level from the coefficient plane, clamped to [-512, 510]
+						// (mdec.c:262-265), as 10-bit two's complement
+						uint32_t word = reinterpret_cast<const uint32_t *>(gp + (pos >> 3) * 32)[(pos >> 1) & 3];
+						uint32_t mag = (pos & 1) ? (word >> 16) : (word & 0xFFFFu);
+						uint2 pq = qp[pos];
+						uint32_t lvl = __umulhi(mag + pq.y, pq.x);
+						int level = neg ? -(int)min(lvl, 0x200u) : (int)min(lvl, 0x1FEu);
+						bw.put(BS_AC_ESCAPE_BITS, (1u << 16) | ((uint32_t)run << 10) | ((uint32_t)level & 0x3FFu));
+					}
 				}
 			}
 			bw.put(2, 2u);   // end of block (mdec.c:502)
@@ -540,8 +553,7 @@ size_t bs_pack_smem_bytes(bool v3, bool smem_stream, int ngroups, int max_size_b
 	size_t padded = (size_t)ngroups * 32;
 	size_t n = 0;
 	if (smem_stream) n += 4 * (size_t)((max_size_bound + 3) / 4 + 2);
-	n += 4 * padded;                     // offs
-	if (v3) n += 4 * padded;             // dcw
+	if (v3) n += 4 * 1024;               // dctab
 	n += 4 * (size_t)(ngroups + 1);      // gtot
 	n += 4 * (8 + 4 * 32);               // misc
 	n += 4 * 64 * 64;                    // vlc
