@@ -48,6 +48,19 @@ __host__ __device__ constexpr int zigzag_at(int i) {
 	return t[i];
 }
 
+__host__ __device__ constexpr int quant_zz_at(int i) {
+	constexpr int t[64] = {BS_QUANT_ZZ_LIST};
+	return t[i];
+}
+
+// Smallest quantiser entry among the AC coefficients of plane row j (zig-zag 8j..8j+7).
+__host__ __device__ constexpr int row_min_quant(int j) {
+	int m = 255;
+	for (int i = 8 * j; i < 8 * j + 8; i++)
+		if (i > 0 && quant_zz_at(i) < m) m = quant_zz_at(i);
+	return m;
+}
+
 void bs_upload_tables() {
 	static uint2 qparam[64 * 64];
 	static uint8_t lenlut[64 * 64];
@@ -94,65 +107,95 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
 	long gid = (long)blockIdx.x * BS_DCT_THREADS + threadIdx.x;
 	int lanes_per_frame = ngroups * 32;
 	int f = (int)(gid / lanes_per_frame);
-	if (f >= n_frames) return;
 	int b = (int)(gid - (long)f * lanes_per_frame);
-	if (b >= nblk) return;
+	// whole warps map to one group of 32 blocks; lanes past the last block idle but stay for
+	// the warp reductions below
+	const bool active = f < n_frames && b < nblk;
 
-	// bitstream order: macroblock columns outermost, rows next, then Cr Cb Y1 Y2 Y3 Y4
-	int mb = b / 6, k = b - 6 * mb;
-	int mx = mb / mbh, my = mb - mx * mbh;
-	const uint8_t *fr = frames + (size_t)f * frame_bytes;
+	uint32_t sign_lo = 0, sign_hi = 0;
+	uint32_t rowq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	uint4 *dst = coefs + (size_t)f * frame_stride_u4 + (size_t)(b >> 5) * (BS_U4_PER_BLOCK * 32) + (b & 31);
 
-	int v[64];
-	if (k < 2) {
-		// interleaved CrCb plane: Cr at even bytes, Cb at odd (mdec.c:627-628)
-		const uint8_t *p = fr + (size_t)width * height + (size_t)width * (my * 8) + mx * 16;
+	if (active) {
+		// bitstream order: macroblock columns outermost, rows next, then Cr Cb Y1 Y2 Y3 Y4
+		int mb = b / 6, k = b - 6 * mb;
+		int mx = mb / mbh, my = mb - mx * mbh;
+		const uint8_t *fr = frames + (size_t)f * frame_bytes;
+
+		int v[64];
+		if (k < 2) {
+			// interleaved CrCb plane: Cr at even bytes, Cb at odd (mdec.c:627-628)
+			const uint8_t *p = fr + (size_t)width * height + (size_t)width * (my * 8) + mx * 16;
 #pragma unroll
-		for (int y = 0; y < 8; y++) {
-			uint4 r = __ldg(reinterpret_cast<const uint4 *>(p + (size_t)y * width));
-			uint32_t w[4] = {r.x, r.y, r.z, r.w};
+			for (int y = 0; y < 8; y++) {
+				uint4 r = __ldg(reinterpret_cast<const uint4 *>(p + (size_t)y * width));
+				uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-			for (int x = 0; x < 8; x++) {
-				uint32_t pair = w[x >> 1] >> (16 * (x & 1));
-				v[8 * y + x] = (int)((k ? (pair >> 8) : pair) & 0xFF);
+				for (int x = 0; x < 8; x++) {
+					uint32_t pair = w[x >> 1] >> (16 * (x & 1));
+					v[8 * y + x] = (int)((k ? (pair >> 8) : pair) & 0xFF);
+				}
+			}
+		} else {
+			int ox = ((k - 2) & 1) * 8, oy = ((k - 2) >> 1) * 8;
+			const uint8_t *p = fr + (size_t)width * (my * 16 + oy) + mx * 16 + ox;
+#pragma unroll
+			for (int y = 0; y < 8; y++) {
+				uint2 r = __ldg(reinterpret_cast<const uint2 *>(p + (size_t)y * width));
+#pragma unroll
+				for (int x = 0; x < 4; x++) {
+					v[8 * y + x] = byte_of(r.x, x);
+					v[8 * y + 4 + x] = byte_of(r.y, x);
+				}
 			}
 		}
-	} else {
-		int ox = ((k - 2) & 1) * 8, oy = ((k - 2) >> 1) * 8;
-		const uint8_t *p = fr + (size_t)width * (my * 16 + oy) + mx * 16 + ox;
+
+		// The reference level-shifts every sample by -128 first (mdec.c:627-632). Both FDCT
+		// variants only ever take differences of samples except in the DC term, where the 64
+		// offsets add up to exactly 8192 through both passes' exact scalings, so the shift is
+		// applied once here.
+		fdct8x8<VARIANT>(v);
+		v[0] -= 8192;
+
 #pragma unroll
-		for (int y = 0; y < 8; y++) {
-			uint2 r = __ldg(reinterpret_cast<const uint2 *>(p + (size_t)y * width));
+		for (int j = 0; j < 8; j++) {
+			uint32_t w[4];
+			uint32_t rowmax = 0;
 #pragma unroll
-			for (int x = 0; x < 4; x++) {
-				v[8 * y + x] = byte_of(r.x, x);
-				v[8 * y + 4 + x] = byte_of(r.y, x);
+			for (int t = 0; t < 4; t++) {
+				int i0 = 8 * j + 2 * t;
+				int c0 = v[zigzag_at(i0)], c1 = v[zigzag_at(i0 + 1)];
+				uint32_t m0 = (uint32_t)abs(c0), m1 = (uint32_t)abs(c1);
+				w[t] = m0 | (m1 << 16);
+				rowmax = max(rowmax, i0 == 0 ? m1 : max(m0, m1));   // the DC term has its own fixed step
+				uint32_t sg = ((uint32_t)c0 >> 31) | (((uint32_t)c1 >> 31) << 1);
+				if (i0 < 32) sign_lo |= sg << i0; else sign_hi |= sg << (i0 - 32);
 			}
+			dst[j * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+			// A coefficient quantises to nonzero at scale q iff 2*|c| >= quant*q, so nothing in
+			// this row survives beyond q = 2*rowmax / (smallest quant of the row).
+			rowq[j] = min(63u, 2u * rowmax / (uint32_t)row_min_quant(j));
 		}
 	}
 
-	// The reference level-shifts every sample by -128 first (mdec.c:627-632). Both FDCT variants
-	// only ever take differences of samples except in the DC term, where the 64 offsets add up
-	// to exactly 8192 through both passes' exact scalings, so the shift is applied once here.
-	fdct8x8<VARIANT>(v);
-	v[0] -= 8192;
-
-	uint4 *dst = coefs + (size_t)f * frame_stride_u4 + (size_t)(b >> 5) * (BS_U4_PER_BLOCK * 32) + (b & 31);
-	uint32_t sign_lo = 0, sign_hi = 0;
+	// per group and plane row: the largest quant scale at which any of the 32 blocks still has a
+	// nonzero coefficient there; the pack kernel skips rows that are dead at its q
+	uint32_t packed_lo = 0, packed_hi = 0;
+#pragma unroll
+	for (int j = 6; j >= 0; j--) rowq[j] = max(rowq[j], rowq[j + 1]);   // a live row keeps its predecessors live
 #pragma unroll
 	for (int j = 0; j < 8; j++) {
-		uint32_t w[4];
-#pragma unroll
-		for (int t = 0; t < 4; t++) {
-			int i0 = 8 * j + 2 * t;
-			int c0 = v[zigzag_at(i0)], c1 = v[zigzag_at(i0 + 1)];
-			w[t] = (uint32_t)abs(c0) | ((uint32_t)abs(c1) << 16);
-			uint32_t s = ((uint32_t)c0 >> 31) | (((uint32_t)c1 >> 31) << 1);
-			if (i0 < 32) sign_lo |= s << i0; else sign_hi |= s << (i0 - 32);
-		}
-		dst[j * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+		uint32_t m = __reduce_max_sync(0xFFFFFFFFu, rowq[j]);
+		if (j < 4) packed_lo |= m << (8 * j); else packed_hi |= m << (8 * (j - 4));
 	}
-	dst[8 * 32] = make_uint4(sign_lo, sign_hi, 0, 0);
+	if (active) {
+		dst[8 * 32] = make_uint4(sign_lo, sign_hi, packed_lo, packed_hi);
+	} else if (f < n_frames) {
+		// padding lanes of the last group: keep the plane fully defined (the pack kernel lets
+		// them run along so that its warps stay convergent)
+#pragma unroll
+		for (int j = 0; j < 9; j++) dst[j * 32] = make_uint4(0, 0, 0, 0);
+	}
 }
 
 // ---- kernel 2: quant-scale search + bit packing ------------------------------------------
@@ -161,6 +204,8 @@ struct PackSmem {
 	uint32_t *stream;   // bitstream image, 32-bit words, first stream bit = bit 31 of word 0
 	uint32_t *dctab;    // v3: DC delta codes, [0..511] chroma, [512..1023] luma (len<<24 | code)
 	uint32_t *gtot;     // per group bit totals -> exclusive group bases
+	uint2 *qpar;        // [2][64] copies of c_qparam rows: [q & 1] holds the current q's
+	uint2 *rowq;        // per group: last live quant scale of each plane row (8 bytes, from bs_dct_kernel)
 	uint32_t *misc;     // [0..2] rotating frame totals, [3] nonzero AC count, [4..] scan scratch
 	uint32_t *vlc;      // [min(level,63)][run] -> (len<<24)|code, see g_vlc
 	uint16_t *lens;     // per block bit length at the current q; after the scan: exclusive offset in its group
@@ -175,21 +220,6 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 	return v;
 }
 
-// Loads magnitude rows [4*HALF, 4*HALF+4) of block (group, lane): coefficients 32*HALF..32*HALF+31.
-template <int HALF>
-__device__ __forceinline__ void load_mags(const uint4 *__restrict__ gp, uint32_t (&w)[16]) {
-#pragma unroll
-	for (int j = 0; j < 4; j++) {
-		uint4 r = gp[(4 * HALF + j) * 32];
-		w[4 * j + 0] = r.x; w[4 * j + 1] = r.y; w[4 * j + 2] = r.z; w[4 * j + 3] = r.w;
-	}
-}
-
-// |coef| number i (0..31) of the loaded half
-__device__ __forceinline__ uint32_t mag_at(const uint32_t (&w)[16], int i) {
-	return (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
-}
-
 // Integer multiply-add pinned to the FMA pipe (IMAD). The pricing loop is bound by the ALU
 // pipe (adds, min/max, compares, shifts-and-adds) while the FMA pipe idles; routing the index,
 // run-length and accumulate arithmetic through IMAD balances the two.
@@ -199,15 +229,48 @@ __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
 	return d;
 }
 
-// AC bit cost of one block at quant scale q (the pricing half of encode_dct_block), half a
-// block (32 coefficients) at a time to keep the register footprint small.
-template <int HALF>
-__device__ __forceinline__ void ac_bits_half(const uint32_t (&w)[16], int q, const uint8_t *lenlut, uint32_t &bits, uint32_t &run) {
-	const uint2 *qp = c_qparam + q * 64 + 32 * HALF;
+// bs_dct_kernel records, per group of 32 blocks and per plane row (8 zig-zag positions), the
+// largest quant scale at which any block of the group still has a nonzero level there. Rows
+// die from the high-frequency end, so a warp only prices / stages the live prefix of rows of
+// its group at the current q; every prefix length has its own straight-line instantiation
+// (rows are fetched up to four at a time to bound the register footprint).
+
+// Leading plane rows to process at quant scale q, rounded up to an instantiated prefix length
+// (0, 2, 4 or 8); rowq bytes are non-increasing in the row index. The same in every lane.
+__device__ __forceinline__ int live_prefix(uint2 rowq, int q) {
+	if ((int)(rowq.y & 0xFFu) >= q) return 8;            // row 4 live
+	if ((int)((rowq.x >> 16) & 0xFFu) >= q) return 4;    // row 2 live
+	return (int)(rowq.x & 0xFFu) >= q ? 2 : 0;           // row 0 live
+}
+
+// Loads N (<= 4) magnitude rows starting at row R0 of block (group, lane).
+template <int R0, int N>
+__device__ __forceinline__ void load_rows(const uint4 *__restrict__ gp, uint32_t (&w)[4 * N]) {
 #pragma unroll
-	for (int i = (HALF ? 0 : 1); i < 32; i++) {
+	for (int j = 0; j < N; j++) {
+		uint4 r = gp[(R0 + j) * 32];
+		w[4 * j + 0] = r.x; w[4 * j + 1] = r.y; w[4 * j + 2] = r.z; w[4 * j + 3] = r.w;
+	}
+}
+
+// |coef| number i of the loaded rows
+template <int N>
+__device__ __forceinline__ uint32_t mag_at(const uint32_t (&w)[4 * N], int i) {
+	return (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
+}
+
+// Prices the AC coefficients of rows R0..R0+N-1 (the pricing half of encode_dct_block).
+// qpar: the current q's (reciprocal, half step) pairs in shared memory.
+template <int R0, int N>
+__device__ __forceinline__ void price_rows(const uint4 *__restrict__ gp, const uint2 *qpar, const uint8_t *lenlut,
+                                           uint32_t &bits, uint32_t &run) {
+	uint32_t w[4 * N];
+	load_rows<R0, N>(gp, w);
+	const uint2 *qp = qpar + 8 * R0;
+#pragma unroll
+	for (int i = (R0 ? 0 : 1); i < 8 * N; i++) {
 		uint2 p = qp[i];
-		uint32_t lv = __umulhi(mag_at(w, i) + p.y, p.x);
+		uint32_t lv = __umulhi(mag_at<N>(w, i) + p.y, p.x);
 		uint32_t m = min(lv, 63u);
 		bits = imad(lenlut[imad(m, 64u, run)], 1u, bits);
 		uint32_t z = imad(lv, 1u, 0xFFFFFFFFu) >> 31;      // 1 when the level is zero (lv < 2^31)
@@ -215,30 +278,53 @@ __device__ __forceinline__ void ac_bits_half(const uint32_t (&w)[16], int q, con
 	}
 }
 
-__device__ __forceinline__ int ac_bits(const uint4 *__restrict__ gp, int q, const uint8_t *lenlut) {
+// AC bit cost of one block whose rows >= NROWS are known to quantise to zero.
+template <int NROWS>
+__device__ __forceinline__ int ac_bits_prefix(const uint4 *__restrict__ gp, const uint2 *qpar, const uint8_t *lenlut) {
 	uint32_t bits = 0, run = 0;
-	uint32_t w[16];
-	load_mags<0>(gp, w);
-	ac_bits_half<0>(w, q, lenlut, bits, run);
-	load_mags<1>(gp, w);
-	ac_bits_half<1>(w, q, lenlut, bits, run);
+	if (NROWS > 0) price_rows<0, (NROWS < 4 ? NROWS : 4)>(gp, qpar, lenlut, bits, run);
+	if (NROWS > 4) price_rows<4, (NROWS > 4 ? NROWS - 4 : 1)>(gp, qpar, lenlut, bits, run);
 	return (int)bits;
 }
 
-// Emit, convergent half: quantise 32 coefficients, park min(level,63) in the thread's column
-// of the level staging area and return the nonzero mask of the half.
-template <int HALF>
-__device__ __forceinline__ uint32_t stage_levels_half(const uint32_t (&w)[16], int q, uint8_t *lev, int lev_stride) {
-	const uint2 *qp = c_qparam + q * 64 + 32 * HALF;
+__device__ __forceinline__ int ac_bits(const uint4 *__restrict__ gp, const uint2 *qpar, const uint2 *cpar, const uint8_t *lenlut, int prefix) {
+	if (prefix == 8) return ac_bits_prefix<8>(gp, cpar, lenlut);   // full blocks: reciprocals via the constant bank
+	if (prefix == 4) return ac_bits_prefix<4>(gp, qpar, lenlut);
+	if (prefix == 2) return ac_bits_prefix<2>(gp, qpar, lenlut);
+	return 0;
+}
+
+// Emit, convergent part: quantise rows R0..R0+N-1, park min(level,63) in the thread's column of
+// the level staging area and return their nonzero mask (bit i = coefficient 8*R0 + i).
+template <int R0, int N>
+__device__ __forceinline__ uint32_t stage_rows(const uint4 *__restrict__ gp, const uint2 *qpar, uint8_t *lev, int lev_stride) {
+	uint32_t w[4 * N];
+	load_rows<R0, N>(gp, w);
+	const uint2 *qp = qpar + 8 * R0;
 	uint32_t nz = 0;
 #pragma unroll
-	for (int i = (HALF ? 0 : 1); i < 32; i++) {
+	for (int i = (R0 ? 0 : 1); i < 8 * N; i++) {
 		uint2 p = qp[i];
-		uint32_t m = min(__umulhi(mag_at(w, i) + p.y, p.x), 63u);
-		lev[(32 * HALF + i) * lev_stride] = (uint8_t)m;
+		uint32_t m = min(__umulhi(mag_at<N>(w, i) + p.y, p.x), 63u);
+		lev[(8 * R0 + i) * lev_stride] = (uint8_t)m;
 		nz = imad(min(m, 1u), 1u << i, nz);
 	}
 	return nz;
+}
+
+template <int NROWS>
+__device__ __forceinline__ void stage_prefix(const uint4 *__restrict__ gp, const uint2 *qpar, uint8_t *lev, int lev_stride,
+                                             uint32_t &nz_lo, uint32_t &nz_hi) {
+	nz_lo = NROWS > 0 ? stage_rows<0, (NROWS < 4 ? (NROWS > 0 ? NROWS : 1) : 4)>(gp, qpar, lev, lev_stride) : 0u;
+	nz_hi = NROWS > 4 ? stage_rows<4, (NROWS > 4 ? NROWS - 4 : 1)>(gp, qpar, lev, lev_stride) : 0u;
+}
+
+__device__ __forceinline__ void stage_levels(const uint4 *__restrict__ gp, const uint2 *qpar, const uint2 *cpar, uint8_t *lev, int lev_stride,
+                                             int prefix, uint32_t &nz_lo, uint32_t &nz_hi) {
+	nz_lo = nz_hi = 0;
+	if (prefix == 8) stage_prefix<8>(gp, cpar, lev, lev_stride, nz_lo, nz_hi);
+	else if (prefix == 4) stage_prefix<4>(gp, qpar, lev, lev_stride, nz_lo, nz_hi);
+	else if (prefix == 2) stage_prefix<2>(gp, qpar, lev, lev_stride, nz_lo, nz_hi);
 }
 
 // Appends MSB-first codes at an arbitrary bit position of the 32-bit-word stream image. Words
@@ -361,14 +447,17 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	PackSmem s;
 	{
 		uint8_t *p = smem_raw;
-		s.lenlut = p;                               p += 64 * 64;
-		s.vlc = reinterpret_cast<uint32_t *>(p);    p += 4 * 64 * 64;
-		s.misc = reinterpret_cast<uint32_t *>(p);   p += 4 * (8 + 4 * 32);
-		s.stream = reinterpret_cast<uint32_t *>(p); if (SMEM_STREAM) p += 4 * (size_t)stream_words;
-		s.dctab = reinterpret_cast<uint32_t *>(p);  if (V3) p += 4 * 1024;
-		s.gtot = reinterpret_cast<uint32_t *>(p);   p += 4 * (size_t)(ngroups + 1);
-		s.lens = reinterpret_cast<uint16_t *>(p);   p += 2 * (size_t)padded;
-		s.dcval = reinterpret_cast<int16_t *>(p);   if (V3) p += 2 * (size_t)padded;
+		auto take = [&](size_t bytes) { uint8_t *at = p; p += (bytes + 15) & ~(size_t)15; return at; };
+		s.lenlut = take(64 * 64);
+		s.vlc = reinterpret_cast<uint32_t *>(take(4 * 64 * 64));
+		s.misc = reinterpret_cast<uint32_t *>(take(4 * (8 + 4 * 32)));
+		s.qpar = reinterpret_cast<uint2 *>(take(8 * 2 * 64));
+		s.stream = reinterpret_cast<uint32_t *>(SMEM_STREAM ? take(4 * (size_t)stream_words) : p);
+		s.dctab = reinterpret_cast<uint32_t *>(V3 ? take(4 * 1024) : p);
+		s.gtot = reinterpret_cast<uint32_t *>(take(4 * (size_t)(ngroups + 1)));
+		s.rowq = reinterpret_cast<uint2 *>(take(8 * (size_t)ngroups));
+		s.lens = reinterpret_cast<uint16_t *>(take(2 * (size_t)padded));
+		s.dcval = reinterpret_cast<int16_t *>(V3 ? take(2 * (size_t)padded) : p);
 		s.lev = p;
 	}
 	const int lev_stride = bs_lev_stride(T);
@@ -385,6 +474,11 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	if (V3) for (int i = tid; i < 1024; i += T) s.dctab[i] = c_dcvlc[i];
 	for (int i = tid; i < words; i += T) stream[i] = 0;
 	if (tid < 8) s.misc[tid] = 0;
+	for (int i = tid; i < 64; i += T) s.qpar[64 + i] = c_qparam[64 + i];   // q = 1
+	for (int g = tid; g < ngroups; g += T) {
+		uint4 r8 = fc[(size_t)g * (BS_U4_PER_BLOCK * 32) + 8 * 32];   // lane 0's sign row carries the group's rowq
+		s.rowq[g] = make_uint2(r8.z, r8.w);
+	}
 	if (V3) {
 		for (int b = tid; b < nblk; b += T) {
 			const uint4 *gp = fc + (size_t)(b >> 5) * (BS_U4_PER_BLOCK * 32) + (b & 31);
@@ -403,11 +497,17 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	uint32_t total_bits = 0;
 	for (; q < 64; q++) {
 		uint32_t mine = 0;
+		// next pass's reciprocals; readers only touch them after this pass's closing barrier
+		if (q < 63)
+			for (int i = tid; i < 64; i += T) s.qpar[((q + 1) & 1) * 64 + i] = c_qparam[(q + 1) * 64 + i];
+		const uint2 *qpar = s.qpar + (q & 1) * 64;
 		for (int g = wid; g < ngroups; g += nw) {
 			int b = g * 32 + lane;
 			int bits = 0;
+			const int prefix = live_prefix(s.rowq[g], q);
 			if (b < nblk) {
-				bits = ac_bits(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane, q, s.lenlut) + 2 + (V3 ? (int)(dc_code(b) >> 24) : 10);
+				bits = ac_bits(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane, qpar, c_qparam + q * 64, s.lenlut, prefix);
+				bits += 2 + (V3 ? (int)(dc_code(b) >> 24) : 10);
 			}
 			s.lens[b] = (uint16_t)bits;
 			mine += bits;
@@ -463,19 +563,16 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	// the thread's shared-memory column and builds a 64-bit nonzero mask; the codes are then
 	// produced by walking the set bits only (runs fall out of the bit positions).
 	{
-		const uint2 *qp = c_qparam + q * 64;
+		const uint2 *qpar = s.qpar + (q & 1) * 64;
 		uint8_t *lev = s.lev + tid;
 		uint32_t nnz = 0;
 		for (int g = wid; g < ngroups; g += nw) {
 			int b = g * 32 + lane;
 			if (b >= nblk) continue;
 			const uint4 *gp = fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane;
-			uint32_t w[16];
-			load_mags<0>(gp, w);
-			const uint32_t dc_mag = w[0] & 0xFFFFu;
-			uint32_t nz_lo = stage_levels_half<0>(w, q, lev, lev_stride);
-			load_mags<1>(gp, w);
-			uint32_t nz_hi = stage_levels_half<1>(w, q, lev, lev_stride);
+			uint32_t nz_lo, nz_hi;
+			const uint32_t dc_mag = reinterpret_cast<const uint32_t *>(gp)[0] & 0xFFFFu;
+			stage_levels(gp, qpar, c_qparam + q * 64, lev, lev_stride, live_prefix(s.rowq[g], q), nz_lo, nz_hi);
 			uint4 sg = gp[8 * 32];
 			BitWriter bw;
 			bw.begin(stream, s.gtot[g] + s.lens[b]);
@@ -508,7 +605,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 						// (mdec.c:262-265), as 10-bit two's complement
 						uint32_t word = reinterpret_cast<const uint32_t *>(gp + (pos >> 3) * 32)[(pos >> 1) & 3];
 						uint32_t mag = (pos & 1) ? (word >> 16) : (word & 0xFFFFu);
-						uint2 pq = qp[pos];
+						uint2 pq = qpar[pos];
 						uint32_t lvl = __umulhi(mag + pq.y, pq.x);
 						int level = neg ? -(int)min(lvl, 0x200u) : (int)min(lvl, 0x1FEu);
 						bw.put(BS_AC_ESCAPE_BITS, (1u << 16) | ((uint32_t)run << 10) | ((uint32_t)level & 0x3FFu));
@@ -552,16 +649,19 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 size_t bs_pack_smem_bytes(bool v3, bool smem_stream, int ngroups, int max_size_bound, int threads) {
 	size_t padded = (size_t)ngroups * 32;
 	size_t n = 0;
-	if (smem_stream) n += 4 * (size_t)((max_size_bound + 3) / 4 + 2);
-	if (v3) n += 4 * 1024;               // dctab
-	n += 4 * (size_t)(ngroups + 1);      // gtot
-	n += 4 * (8 + 4 * 32);               // misc
-	n += 4 * 64 * 64;                    // vlc
-	n += 2 * padded;                     // lens
-	if (v3) n += 2 * padded;             // dcval
-	n += 64 * 64;                        // lenlut
-	n += 64 * (size_t)bs_lev_stride(threads);   // lev
-	return (n + 15) & ~(size_t)15;
+	auto take = [&](size_t bytes) { n += (bytes + 15) & ~(size_t)15; };
+	take(64 * 64);                        // lenlut
+	take(4 * 64 * 64);                    // vlc
+	take(4 * (8 + 4 * 32));               // misc
+	take(8 * 2 * 64);                     // qpar
+	if (smem_stream) take(4 * (size_t)((max_size_bound + 3) / 4 + 2));
+	if (v3) take(4 * 1024);               // dctab
+	take(4 * (size_t)(ngroups + 1));      // gtot
+	take(8 * (size_t)ngroups);            // rowq
+	take(2 * padded);                     // lens
+	if (v3) take(2 * padded);             // dcval
+	take(64 * (size_t)bs_lev_stride(threads));   // lev
+	return n;
 }
 
 cudaError_t bs_launch_dct(int fdct_variant, const uint8_t *d_frames, size_t frame_bytes, int n, int width, int height,

@@ -136,6 +136,7 @@ def emit(path, prefix, guard):
     out.append("#define %sZIGZAG_LIST %s\n" % (prefix, ", ".join(str(z) for z in zz)))
     out.append("/* quantiser matrix, raster order (mdec.c:189-198) */")
     out.append("static const uint8_t %sQUANT[64] = {\n%s\n};\n" % (prefix, fmt_array(QUANT, 8, "%2d")))
+    out.append("#define %sQUANT_ZZ_LIST %s\n" % (prefix, ", ".join(str(QUANT[z]) for z in zz)))
     out.append("/* quantiser matrix in zig-zag order */")
     out.append("static const uint8_t %sQUANT_ZZ[64] = {\n%s\n};\n" % (prefix, fmt_array([QUANT[z] for z in zz], 8, "%2d")))
     out.append("/* [run][|level|] -> (nbits<<24)|code with sign bit clear; 0 = escape (mdec.c:39-157, 278-284) */")
