@@ -209,6 +209,25 @@ int psxb200_bs_encode_host(psxb200_bs_encoder_t *enc, int n, const uint8_t *h_fr
                            const int *h_max_sizes, uint8_t *h_out, size_t out_stride,
                            psxb200_bs_result_t *h_results);
 
+/* STR video sectors straight from the GPU: what calling
+ * encode_sector_str (mdec.c:757-836) once per sector produces for a video-only stream driven as
+ * encode_file_strspu does (filefmt.c:546-630). Frame k of the call has frame_index
+ * first_frame_index + k (1-based, mdec.c:769) and the byte budget
+ * 2016 * (floor(K*num/den) - floor((K-1)*num/den)), K its frame_index — the closed form of the
+ * overflow accumulator (mdec.c:772-774) with num = frame_block_base_overflow,
+ * den = frame_block_overflow_den. Each frame becomes budget/2016 sectors: the 32-byte STR
+ * header at the format's offset (FORMAT_STRV: 2048-byte sectors, offset 0; FORMAT_STR: 2336,
+ * offset 8; FORMAT_STRCD: 2352, offset 0x18; mdec.c:824-829) followed by a 2016-byte slice. Other
+ * bytes of a sector are not written (as in the reference; the caller's mux adds subheaders
+ * and EDC, filefmt.c:463-475). psxb200_str_sector_count gives the number of sectors. */
+long long psxb200_str_sector_count(int n_frames, int first_frame_index, int sectors_num, int sectors_den);
+int psxb200_str_encode_device(psxb200_bs_encoder_t *enc, int n, const uint8_t *d_frames, int format,
+                              int first_frame_index, int sectors_num, int sectors_den, int video_id,
+                              uint8_t *d_sectors, psxb200_bs_result_t *d_results, void *stream);
+int psxb200_str_encode_host(psxb200_bs_encoder_t *enc, int n, const uint8_t *h_frames, int format,
+                            int first_frame_index, int sectors_num, int sectors_den, int video_id,
+                            uint8_t *h_sectors, psxb200_bs_result_t *h_results);
+
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 unsigned long long psxb200_launch_count(void);
 

@@ -89,6 +89,9 @@ SYMBOLS = {
     "psxb200_bs_timing_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "psxb200_bs_encode_device": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, C.c_size_t, _P, _P]),
     "psxb200_bs_encode_host": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "psxb200_str_sector_count": (C.c_longlong, [C.c_int] * 4),
+    "psxb200_str_encode_device": (C.c_int, [_P, C.c_int, _P] + [C.c_int] * 5 + [_P, _P, _P]),
+    "psxb200_str_encode_host": (C.c_int, [_P, C.c_int, _P] + [C.c_int] * 5 + [_P, _P]),
     "psxb200_spu_encode_device": (C.c_int, [C.c_int, _P, C.c_int, C.c_long, C.c_int, _P, _P, _P, C.c_long, _P]),
     "psxb200_spu_encode_host": (C.c_int, [C.c_int, _P, C.c_int, C.c_long, C.c_int, _P, _P, C.c_long]),
     "psxb200_xa_encode_device": (C.c_int, [C.c_int] * 7 + [_P, C.c_long, C.c_int, C.c_int, _P, _P, C.c_long, _P]),
@@ -186,6 +189,20 @@ class BsEncoder:
         """Host buffers by address (numpy / pinned torch tensors); returns number of failed frames."""
         return _check(lib().psxb200_bs_encode_host(self.handle, n, _ptr(h_frames), _ptr(h_max_sizes), _ptr(h_out),
                                                    out_stride, _ptr(h_results)), "bs_encode_host")
+
+    def str_encode_host(self, frames, first_frame_index, sectors_num, sectors_den, fmt=FORMAT_STRV, video_id=0x8001,
+                        sectors=None):
+        """psxb200_str_encode_host -> (sectors[n_sectors, sector_size] uint8, res[n, 4] int32)."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8).reshape(-1, self.frame_bytes)
+        n = frames.shape[0]
+        count = int(lib().psxb200_str_sector_count(n, first_frame_index, sectors_num, sectors_den))
+        size = {FORMAT_STRV: 2048, FORMAT_STR: 2336, FORMAT_STRCD: 2352}[fmt]
+        if sectors is None:
+            sectors = np.zeros((count, size), dtype=np.uint8)
+        res = np.zeros((n, 4), dtype=np.int32)
+        _check(lib().psxb200_str_encode_host(self.handle, n, frames.ctypes.data, fmt, first_frame_index, sectors_num,
+                                             sectors_den, video_id, sectors.ctypes.data, res.ctypes.data), "str_encode_host")
+        return sectors, res
 
     def encode_host(self, frames, max_sizes, stride=None):
         """frames: uint8 [n, 1.5*W*H]; -> (out[n, stride] uint8, res[n, 4] int32)."""

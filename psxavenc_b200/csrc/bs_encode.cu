@@ -436,7 +436,8 @@ template <bool V3, bool SMEM_STREAM, int MAX_THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS)
 bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk, int ngroups, int nmb, int codec,
                const int *__restrict__ max_sizes, int max_size_bound, uint8_t *__restrict__ out, size_t out_stride,
-               psxb200_bs_result_t *__restrict__ results, uint32_t *__restrict__ gstream, size_t gstream_stride) {
+               psxb200_bs_result_t *__restrict__ results, uint32_t *__restrict__ gstream, size_t gstream_stride,
+               const BsStrLayout str) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
 	const int f = blockIdx.x;
@@ -464,8 +465,12 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	uint32_t *stream = SMEM_STREAM ? s.stream : gstream + (size_t)f * gstream_stride;
 
 	const uint4 *fc = coefs + (size_t)f * frame_stride_u4;
-	int max_size = max_sizes[f];
+	// STR mode: budget and sector position follow from the frame index alone
+	const long long str_k = (long long)str.frame_index0 + f;
+	const long long str_before = str.sector_size ? (str_k - 1) * str.sectors_num / str.sectors_den : 0;
+	int max_size = str.sector_size ? (int)(str_k * str.sectors_num / str.sectors_den - str_before) * 2016 : max_sizes[f];
 	if (max_size > max_size_bound) max_size = 0;   // contract violation -> frame fails
+	if (str.sector_size) out += (size_t)(str_before - str.sector0) * str.sector_size - (size_t)f * out_stride;
 	const int words = max_size > 0 ? (max_size + 3) / 4 + 2 : 0;
 
 	for (int i = tid; i < 64 * 64 / 4; i += T)
@@ -523,9 +528,36 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	}
 
 	uint32_t *out32 = reinterpret_cast<uint32_t *>(out + (size_t)f * out_stride);
+	// destination of 32-bit word i of the frame's bitstream buffer: contiguous, or sliced into
+	// 2016-byte sector payloads behind their 32-byte headers (mdec.c:831-832)
+	auto word_at = [&](int i) -> uint32_t * {
+		if (!str.sector_size) return out32 + i;
+		int j = i / 504;
+		return reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(out32) + (size_t)j * str.sector_size +
+		                                    str.header_offset + 32) + (i - 504 * j);
+	};
+	// STR sector headers (mdec.c:782-820)
+	auto write_str_headers = [&](uint32_t bytes_used, uint32_t bs0, uint32_t bs1) {
+		const int chunks = max_size / 2016;
+		for (int j = tid; j < chunks; j += T) {
+			uint32_t *h = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(out32) + (size_t)j * str.sector_size +
+			                                           str.header_offset);
+			h[0] = 0x0160u | ((uint32_t)(str.video_id & 0xFFFF) << 16);
+			h[1] = (uint32_t)j | ((uint32_t)chunks << 16);
+			h[2] = (uint32_t)str_k;
+			h[3] = bytes_used;
+			h[4] = (uint32_t)(str.width & 0xFFFF) | ((uint32_t)(str.height & 0xFFFF) << 16);
+			h[5] = bs0;
+			h[6] = bs1;
+			h[7] = 0;
+		}
+	};
 	if (q >= 64) {
-		for (int i = tid; i < (max_size >> 2); i += T) out32[i] = 0;
-		for (int i = (max_size & ~3) + tid; i < max_size; i += T) out[(size_t)f * out_stride + i] = 0;
+		for (int i = tid; i < (max_size >> 2); i += T) *word_at(i) = 0;
+		if (!str.sector_size)
+			for (int i = (max_size & ~3) + tid; i < max_size; i += T) out[(size_t)f * out_stride + i] = 0;
+		else
+			write_str_headers(0, 0, 0);
 		if (tid == 0) results[f] = psxb200_bs_result_t{0, 0, 64, 0};
 		return;
 	}
@@ -634,9 +666,10 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		if (i == 0) v = hdr0;
 		else if (i == 1) v = hdr1;
 		else { uint32_t x = stream[i - 2]; v = (x >> 16) | (x << 16); }
-		out32[i] = v;
+		*word_at(i) = v;
 	}
-	if (tid < (max_size & 3)) {
+	if (str.sector_size) write_str_headers((uint32_t)((8 + 2 * units + 3) & ~3), hdr0, hdr1);
+	if (!str.sector_size && tid < (max_size & 3)) {
 		int i = (max_size & ~3) + tid;   // >= 8 here, since the frame fitted
 		uint32_t x = stream[(i >> 2) - 2];
 		uint32_t v = (x >> 16) | (x << 16);
@@ -681,7 +714,7 @@ template <bool V3, bool SMEM_STREAM, int MAX_THREADS, int MIN_CTAS>
 static cudaError_t launch_pack_t(int threads, size_t smem, int n, const uint4 *d_coefs, const BsGeometry &geo, int codec,
                                  const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
                                  psxb200_bs_result_t *d_results, uint32_t *d_gstream, size_t gstream_stride,
-                                 cudaStream_t stream) {
+                                 const BsStrLayout &str, cudaStream_t stream) {
 	auto kern = bs_pack_kernel<V3, SMEM_STREAM, MAX_THREADS, MIN_CTAS>;
 	static size_t configured = 0;
 	if (smem > configured) {
@@ -691,7 +724,7 @@ static cudaError_t launch_pack_t(int threads, size_t smem, int n, const uint4 *d
 	}
 	kern<<<n, threads, smem, stream>>>(d_coefs, geo.frame_stride_u4, geo.nblk, geo.ngroups, geo.mbw * geo.mbh, codec,
 	                                   d_max_sizes, max_size_bound, d_out, out_stride, d_results, d_gstream,
-	                                   gstream_stride);
+	                                   gstream_stride, str);
 	return cudaGetLastError();
 }
 
@@ -699,9 +732,10 @@ template <int MAX_THREADS, int MIN_CTAS>
 static cudaError_t launch_pack_cfg(bool v3, bool smem_stream, int threads, size_t smem, int n, const uint4 *d_coefs,
                                    const BsGeometry &geo, int codec, const int *d_max_sizes, int max_size_bound,
                                    uint8_t *d_out, size_t out_stride, psxb200_bs_result_t *d_results,
-                                   uint32_t *d_gstream, size_t gstream_stride, cudaStream_t stream) {
+                                   uint32_t *d_gstream, size_t gstream_stride, const BsStrLayout &str,
+                                   cudaStream_t stream) {
 #define PSXB200_PACK_ARGS threads, smem, n, d_coefs, geo, codec, d_max_sizes, max_size_bound, d_out, out_stride, \
-	d_results, d_gstream, gstream_stride, stream
+	d_results, d_gstream, gstream_stride, str, stream
 	if (v3)
 		return smem_stream ? launch_pack_t<true, true, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
 		                   : launch_pack_t<true, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
@@ -713,12 +747,12 @@ static cudaError_t launch_pack_cfg(bool v3, bool smem_stream, int threads, size_
 cudaError_t bs_launch_pack(int codec, int threads, int min_ctas, int n, const uint4 *d_coefs, const BsGeometry &geo,
                            const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
                            psxb200_bs_result_t *d_results, uint32_t *d_gstream, size_t gstream_stride,
-                           cudaStream_t stream) {
+                           const BsStrLayout &str, cudaStream_t stream) {
 	bool v3 = codec != 0;
 	bool smem_stream = d_gstream == nullptr;
 	size_t smem = bs_pack_smem_bytes(v3, smem_stream, geo.ngroups, max_size_bound, threads);
 #define PSXB200_CFG_ARGS v3, smem_stream, threads, smem, n, d_coefs, geo, codec, d_max_sizes, max_size_bound, d_out, \
-	out_stride, d_results, d_gstream, gstream_stride, stream
+	out_stride, d_results, d_gstream, gstream_stride, str, stream
 	// register budget variants: (max threads per CTA, CTAs per SM the register file must hold)
 	if (threads <= 320) {
 		if (min_ctas >= 4) return launch_pack_cfg<320, 4>(PSXB200_CFG_ARGS);

@@ -30,6 +30,21 @@ struct BsGeometry {
 		  frame_stride_u4((size_t)((6 * (width / 16) * (height / 16) + 31) / 32) * BS_U4_PER_BLOCK * 32) {}
 };
 
+// STR sector output mode of the pack kernel (encode_sector_str, mdec.c:757-836, driven as
+// encode_file_strspu does for a video-only stream, filefmt.c:546-630). sector_size == 0: off.
+// Frame f of a launch has frame_index K = frame_index0 + f (1-based, mdec.c:769), the byte
+// budget 2016 * (floor(K*num/den) - floor((K-1)*num/den)) (mdec.c:772-774 in closed form) and
+// its sectors start at sector floor((K-1)*num/den) - sector0 of the output buffer.
+struct BsStrLayout {
+	int sector_size;        // bytes between consecutive sectors
+	int header_offset;      // offset of the 32-byte STR header inside a sector (mdec.c:824-829)
+	int frame_index0;       // frame_index of the launch's first frame
+	int sectors_num;        // frame_block_base_overflow
+	int sectors_den;        // frame_block_overflow_den
+	long long sector0;      // floor((first frame_index of the batch - 1) * num / den)
+	int video_id, width, height;
+};
+
 void bs_upload_tables();
 size_t bs_pack_smem_bytes(bool v3, bool smem_stream, int ngroups, int max_size_bound, int threads);
 
@@ -47,6 +62,6 @@ cudaError_t bs_launch_dct(int fdct_variant, const uint8_t *d_frames, size_t fram
 cudaError_t bs_launch_pack(int codec, int threads, int min_ctas, int n, const uint4 *d_coefs, const BsGeometry &geo,
                            const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
                            psxb200_bs_result_t *d_results, uint32_t *d_gstream, size_t gstream_stride,
-                           cudaStream_t stream);
+                           const BsStrLayout &str, cudaStream_t stream);
 
 }  // namespace psxb200

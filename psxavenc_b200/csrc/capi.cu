@@ -171,7 +171,7 @@ extern "C" void psxb200_bs_destroy(psxb200_bs_encoder_t *enc) {
 
 static int bs_encode_chunked(psxb200_bs_encoder *enc, uint4 *d_coefs, int n, const uint8_t *d_frames,
                              const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
-                             psxb200_bs_result_t *d_results, cudaStream_t stream) {
+                             psxb200_bs_result_t *d_results, cudaStream_t stream, const BsStrLayout *str_batch = nullptr) {
 	uint32_t *gstream = nullptr;
 	size_t gstride = 0;
 	if (bs_pack_smem_bytes(enc->codec != 0, true, enc->geo.ngroups, max_size_bound, enc->pack_threads) > BS_SMEM_BUDGET) {
@@ -185,9 +185,15 @@ static int bs_encode_chunked(psxb200_bs_encoder *enc, uint4 *d_coefs, int n, con
 		CU_TRY(bs_launch_dct(enc->fdct, d_frames + (size_t)first * enc->frame_bytes, enc->frame_bytes, m, enc->width,
 		                     enc->height, enc->geo, d_coefs, stream));
 		if (enc->timing) CU_TRY(enc->mark(stream));
-		CU_TRY(bs_launch_pack(enc->codec, enc->pack_threads, enc->pack_min_ctas, m, d_coefs, enc->geo, d_max_sizes + first, max_size_bound,
-		                      d_out + (size_t)first * out_stride, out_stride, d_results + first, gstream, gstride,
-		                      stream));
+		BsStrLayout str{};
+		if (str_batch) {
+			str = *str_batch;
+			str.frame_index0 += first;   // sector0 stays the batch's: the kernel positions frames absolutely
+		}
+		CU_TRY(bs_launch_pack(enc->codec, enc->pack_threads, enc->pack_min_ctas, m, d_coefs, enc->geo,
+		                      str_batch ? nullptr : d_max_sizes + first, max_size_bound,
+		                      str_batch ? d_out : d_out + (size_t)first * out_stride, out_stride, d_results + first, gstream,
+		                      gstride, str, stream));
 		if (enc->timing) CU_TRY(enc->mark(stream));
 		g_launches += 2;
 	}
@@ -267,6 +273,95 @@ extern "C" int psxb200_bs_encode_host(psxb200_bs_encoder_t *enc, int n, const ui
 			return -1;
 		CU_TRY(cudaMemcpy2DAsync(h_out + (size_t)first * out_stride, std::max(out_stride, (size_t)bound), enc->out[slot].ptr,
 		                         dstride, (size_t)bound, m, cudaMemcpyDeviceToHost, st));
+		CU_TRY(cudaMemcpyAsync(h_results + first, enc->res[slot].ptr, (size_t)m * sizeof(psxb200_bs_result_t),
+		                       cudaMemcpyDeviceToHost, st));
+	}
+	CU_TRY(cudaStreamSynchronize(enc->streams[0]));
+	CU_TRY(cudaStreamSynchronize(enc->streams[1]));
+	int failed = 0;
+	for (int i = 0; i < n; i++) failed += h_results[i].quant_scale >= 64;
+	return failed;
+}
+
+// ---- STR video sectors -------------------------------------------------
+
+static int str_layout(psxb200_bs_encoder *enc, int format, int first_frame_index, int sectors_num, int sectors_den,
+                      int video_id, BsStrLayout *out) {
+	if (first_frame_index < 1 || sectors_num < 1 || sectors_den < 1)
+		return fail("psxb200_str_*: first_frame_index, sectors_num and sectors_den must be >= 1");
+	BsStrLayout l{};
+	// sector size / header offset per container (mdec.c:824-829; filefmt.c:453,502,572,613)
+	if (format == FORMAT_STRV) { l.sector_size = 2048; l.header_offset = 0; }
+	else if (format == FORMAT_STR) { l.sector_size = 2336; l.header_offset = 8; }
+	else if (format == FORMAT_STRCD) { l.sector_size = 2352; l.header_offset = 0x18; }
+	else return fail("psxb200_str_*: format must be FORMAT_STR, FORMAT_STRCD or FORMAT_STRV");
+	l.frame_index0 = first_frame_index;
+	l.sectors_num = sectors_num;
+	l.sectors_den = sectors_den;
+	l.sector0 = (long long)(first_frame_index - 1) * sectors_num / sectors_den;
+	l.video_id = video_id;
+	l.width = enc->width;
+	l.height = enc->height;
+	*out = l;
+	return 0;
+}
+
+extern "C" long long psxb200_str_sector_count(int n_frames, int first_frame_index, int sectors_num, int sectors_den) {
+	long long a = (long long)(first_frame_index - 1) * sectors_num / sectors_den;
+	long long b = (long long)(first_frame_index - 1 + n_frames) * sectors_num / sectors_den;
+	return b - a;
+}
+
+extern "C" int psxb200_str_encode_device(psxb200_bs_encoder_t *enc, int n, const uint8_t *d_frames, int format,
+                                         int first_frame_index, int sectors_num, int sectors_den, int video_id,
+                                         uint8_t *d_sectors, psxb200_bs_result_t *d_results, void *stream) {
+	if (!enc) return fail("psxb200_str_encode_device: NULL encoder");
+	if (n <= 0) return 0;
+	BsStrLayout l;
+	if (str_layout(enc, format, first_frame_index, sectors_num, sectors_den, video_id, &l)) return -1;
+	if (((uintptr_t)d_frames & 15) || ((uintptr_t)d_sectors & 3))
+		return fail("psxb200_str_encode_device: alignment contract violated (frames 16 bytes, sectors 4 bytes)");
+	int bound = 2016 * ((sectors_num + sectors_den - 1) / sectors_den);
+	return bs_encode_chunked(enc, enc->coefs[0].ptr, n, d_frames, nullptr, bound, d_sectors, 0, d_results,
+	                         static_cast<cudaStream_t>(stream), &l);
+}
+
+extern "C" int psxb200_str_encode_host(psxb200_bs_encoder_t *enc, int n, const uint8_t *h_frames, int format,
+                                       int first_frame_index, int sectors_num, int sectors_den, int video_id,
+                                       uint8_t *h_sectors, psxb200_bs_result_t *h_results) {
+	if (!enc) return fail("psxb200_str_encode_host: NULL encoder");
+	if (n <= 0) return 0;
+	BsStrLayout batch;
+	if (str_layout(enc, format, first_frame_index, sectors_num, sectors_den, video_id, &batch)) return -1;
+	for (int i = 0; i < 2; i++) {
+		if (!enc->streams[i]) CU_TRY(cudaStreamCreateWithFlags(&enc->streams[i], cudaStreamNonBlocking));
+	}
+	const int hc = enc->host_chunk;
+	const int bound = 2016 * ((sectors_num + sectors_den - 1) / sectors_den);
+	CU_TRY(enc->coefs[1].reserve((size_t)hc * enc->geo.frame_stride_u4));
+	for (int first = 0, chunk = 0; first < n; first += hc, chunk++) {
+		int slot = chunk & 1;
+		int m = std::min(hc, n - first);
+		cudaStream_t st = enc->streams[slot];
+		// this chunk as a batch of its own: sectors land at the start of the slot's buffer
+		BsStrLayout l;
+		if (str_layout(enc, format, first_frame_index + first, sectors_num, sectors_den, video_id, &l)) return -1;
+		long long sectors = psxb200_str_sector_count(m, first_frame_index + first, sectors_num, sectors_den);
+		long long before = l.sector0 - batch.sector0;
+		size_t bytes = (size_t)sectors * l.sector_size;
+		CU_TRY(cudaStreamSynchronize(st));
+		CU_TRY(enc->in[slot].reserve((size_t)hc * enc->frame_bytes));
+		CU_TRY(enc->out[slot].reserve((size_t)(psxb200_str_sector_count(hc, 1, sectors_num, sectors_den) + 2) * l.sector_size));
+		CU_TRY(enc->res[slot].reserve(hc));
+		CU_TRY(cudaMemcpyAsync(enc->in[slot].ptr, h_frames + (size_t)first * enc->frame_bytes, (size_t)m * enc->frame_bytes,
+		                       cudaMemcpyHostToDevice, st));
+		// bytes encode_sector_str never writes (outside header + payload) keep the caller's content
+		if (l.sector_size != 2048)
+			CU_TRY(cudaMemcpyAsync(enc->out[slot].ptr, h_sectors + (size_t)before * l.sector_size, bytes, cudaMemcpyHostToDevice, st));
+		if (bs_encode_chunked(enc, enc->coefs[slot].ptr, m, enc->in[slot].ptr, nullptr, bound, enc->out[slot].ptr, 0,
+		                      enc->res[slot].ptr, st, &l))
+			return -1;
+		CU_TRY(cudaMemcpyAsync(h_sectors + (size_t)before * l.sector_size, enc->out[slot].ptr, bytes, cudaMemcpyDeviceToHost, st));
 		CU_TRY(cudaMemcpyAsync(h_results + first, enc->res[slot].ptr, (size_t)m * sizeof(psxb200_bs_result_t),
 		                       cudaMemcpyDeviceToHost, st));
 	}
