@@ -1,0 +1,63 @@
+"""Multi-GPU (NCCL) test of the sharded encode: needs >= 2 CUDA devices, skipped otherwise
+(the driver's single-GPU test box skips it; bench.py --gpus N exercises the same code)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, queue):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import oracle
+    import psxavenc_b200 as pb
+    from psxavenc_b200 import sharding, synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    try:
+        w, h, n = 320, 240, 21
+        frames = synth.gen_frames(0, n, w, h, 3)
+        budgets = sharding.frame_budgets(n, 1050, 120)
+        first, last = sharding.frame_range(n, rank, world)
+        enc = pb.BsEncoder(0, w, h, pb.FDCT_ISLOW, max_batch=8)
+        m = last - first
+        d_frames = torch.from_numpy(frames[first:last]).cuda()
+        d_sizes = torch.from_numpy(budgets[first:last]).cuda()
+        d_out = torch.zeros((m, 18144), dtype=torch.uint8, device="cuda")
+        d_res = torch.zeros((m, 4), dtype=torch.int32, device="cuda")
+        enc.encode_device(m, d_frames, d_sizes, 18144, d_out, 18144, d_res, torch.cuda.current_stream().cuda_stream)
+        all_res = sharding.gather_results(d_res, n, dist)
+        outs = [None] * world
+        dist.all_gather_object(outs, d_out.cpu().numpy())
+        if rank == 0:
+            exp_out, exp_res = oracle.Restated().bs_encode_batch(0, w, h, frames, budgets, oracle.FDCT_ISLOW, stride=18144)
+            queue.put(bool(np.array_equal(all_res.cpu().numpy(), exp_res) and np.array_equal(np.concatenate(outs), exp_out)))
+        enc.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_encode_matches_oracle():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert queue.get(timeout=5) is True
