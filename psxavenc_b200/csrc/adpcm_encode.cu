@@ -107,14 +107,27 @@ __device__ __forceinline__ void encode_unit(const int (&s)[UNIT], int qerr, int 
 	header = __shfl_sync(0xFFFFFFFFu, (sh & 0x0F) | (filter << 4), winner, 16);
 }
 
-__device__ __forceinline__ void load_unit(const int16_t *__restrict__ src, long pitch, int limit, int (&s)[UNIT]) {
+// Samples of one 28-sample unit, spread over the 16 lanes of a half-warp: lane `sub` holds
+// samples sub and sub+16. Fetching the NEXT unit this way (2 coalesced loads per lane) while the
+// current one is being searched takes the global-memory latency off the serial chain; the
+// values are then broadcast to every lane with shuffles (each candidate needs all 28).
+struct UnitFetch { int a, b; };
+
+__device__ __forceinline__ UnitFetch fetch_unit(const int16_t *__restrict__ src, long pitch, int limit, int sub) {
+	UnitFetch f;
+	f.a = sub < limit ? (int)__ldg(src + sub * pitch) : 0;
+	f.b = (sub + 16 < UNIT && sub + 16 < limit) ? (int)__ldg(src + (sub + 16) * pitch) : 0;
+	return f;
+}
+
+__device__ __forceinline__ void spread_unit(const UnitFetch &f, int (&s)[UNIT]) {
 #pragma unroll
-	for (int i = 0; i < UNIT; i++) s[i] = i < limit ? (int)__ldg(src + i * pitch) : 0;
+	for (int i = 0; i < UNIT; i++) s[i] = __shfl_sync(0xFFFFFFFFu, i < 16 ? f.a : f.b, i & 15, 16);
 }
 
 // ---- SPU ---------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(ADPCM_THREADS)
+__global__ void __launch_bounds__(ADPCM_THREADS, 8)
 adpcm_spu_kernel(int n_streams, const int16_t *__restrict__ samples, int pitch, long group_stride, int sample_count,
                  const int *__restrict__ counts, ChannelState *__restrict__ states, uint8_t *__restrict__ out,
                  long out_stride) {
@@ -136,10 +149,12 @@ adpcm_spu_kernel(int n_streams, const int16_t *__restrict__ samples, int pitch, 
 	unsigned long long mse = st.mse;
 	uint8_t *dst = out + (long)(live ? stream : 0) * out_stride;
 
+	UnitFetch next = fetch_unit(src, pitch, count, sub);
 	for (int u = 0; u < warp_units; u++) {
 		const bool active = u < units;
 		int s[UNIT];
-		load_unit(src + (long)u * UNIT * pitch, pitch, active ? count - u * UNIT : 0, s);
+		spread_unit(next, s);
+		next = fetch_unit(src + (long)(u + 1) * UNIT * pitch, pitch, u + 1 < units ? count - (u + 1) * UNIT : 0, sub);
 		uint32_t codes[4];
 		unsigned long long m;
 		int header;
@@ -168,7 +183,7 @@ adpcm_spu_kernel(int n_streams, const int16_t *__restrict__ samples, int pitch, 
 // ---- XA ----------------------------------------------------------------------------------
 
 template <int BITS>   // 4 or 8
-__global__ void __launch_bounds__(ADPCM_THREADS)
+__global__ void __launch_bounds__(ADPCM_THREADS, 8)
 adpcm_xa_kernel(int n_streams, int stereo, int sector_size, const int16_t *__restrict__ samples, long in_stride,
                 int sample_count, ChannelState *__restrict__ states, uint8_t *__restrict__ out, long out_stride) {
 	constexpr int RANGE = BITS == 4 ? 12 : 8;
@@ -192,16 +207,22 @@ adpcm_xa_kernel(int n_streams, int stereo, int sector_size, const int16_t *__res
 	const bool chain = stereo || half == 0;
 	const int steps = stereo ? UNITS / 2 : UNITS;   // sequential units per chain per group
 
-	for (int j = 0; j < groups; j++) {
+	// unit (j, step) of this half-warp's chain: source pointer and sample limit. Stereo: the
+	// pointer advances 56 interleaved samples per L/R pair but the limit only drops by 28
+	// (adpcm.c:204-211); mono: 28 and 28.
+	auto fetch = [&](int j, int step) {
 		const int16_t *gsrc = base + (long)j * JUMP;
-		const int limit0 = total - j * JUMP;
+		const int16_t *src = stereo ? gsrc + 56 * step + half : gsrc + 28 * step;
+		int limit = (chain && j < groups) ? total - j * JUMP - 28 * step : 0;
+		return fetch_unit(src, stereo ? 2 : 1, limit, sub);
+	};
+	UnitFetch next = fetch(0, 0);
+	for (int j = 0; j < groups; j++) {
 		for (int step = 0; step < steps; step++) {
-			// stereo: pointer advances 56 interleaved samples per L/R pair but the limit only
-			// drops by 28 (adpcm.c:204-211); mono: 28 and 28
-			const int16_t *src = stereo ? gsrc + 56 * step + half : gsrc + 28 * step;
 			const int unit = stereo ? 2 * step + half : step;
 			int s[UNIT];
-			load_unit(src, stereo ? 2 : 1, chain ? limit0 - 28 * step : 0, s);
+			spread_unit(next, s);
+			next = step + 1 < steps ? fetch(j, step + 1) : fetch(j + 1, 0);
 			uint32_t codes[BITS == 4 ? 4 : 7];
 			unsigned long long m;
 			int header;
