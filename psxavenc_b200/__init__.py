@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpsxav_b200.so")
+# PSXB200_LIB points at an alternative build of the same library (A/B experiments)
+LIB_PATH = os.environ.get("PSXB200_LIB") or os.path.join(HERE, "libpsxav_b200.so")
 
 FDCT_ISLOW, FDCT_SSE2 = 0, 1
 CODEC_V2, CODEC_V3, CODEC_V3DC = 0, 1, 2

@@ -101,7 +101,7 @@ void bs_upload_tables() {
 __device__ __forceinline__ int byte_of(uint32_t w, int k) { return (int)((w >> (8 * k)) & 0xFF); }
 
 template <int VARIANT>
-__global__ void __launch_bounds__(BS_DCT_THREADS)
+__global__ void __launch_bounds__(BS_DCT_THREADS, BS_DCT_MIN_CTAS)
 bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_frames, int width, int height,
               int mbh, int nblk, int ngroups, uint4 *__restrict__ coefs, size_t frame_stride_u4) {
 	long gid = (long)blockIdx.x * BS_DCT_THREADS + threadIdx.x;
