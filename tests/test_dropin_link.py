@@ -82,3 +82,64 @@ def test_driver_spui_loop(driver, restated, tmp_path):
         done += length
         k += 1
     assert np.array_equal(got, np.concatenate(chunks))
+
+
+def _mux_strcd(lib, frames, pcm, n_sectors, w, h):
+    """The sector schedule of encode_file_str (filefmt.c:391-520) for -t strcd defaults: 2x speed,
+    15 fps, 37800 Hz 4-bit stereo XA -> interleave 8 (1 audio + 7 video sectors), driven through
+    the drop-in symbols of `lib` (ours or the reference build). Sector init / EDC of video
+    sectors belong to filefmt.c + cdrom.c (out of scope) and are left out on both sides."""
+    import ctypes as C
+    import psxavenc_b200 as pb
+    settings_cls = pb.XaSettings
+    xa = settings_cls(1, True, 37800, 4, 1, 0)                      # XACD sectors
+    interleave, video_per_block, per_sector = 8, 7, 2016
+    enc = pb.MdecEncoder()
+    lib.init_mdec_encoder.restype = C.c_bool
+    lib.init_mdec_encoder.argtypes = [C.POINTER(pb.MdecEncoder), C.c_int, C.c_int, C.c_int]
+    lib.encode_sector_str.restype = C.c_int
+    lib.encode_sector_str.argtypes = [C.POINTER(pb.MdecEncoder), C.c_int, C.c_uint16, C.c_void_p, C.c_void_p]
+    lib.destroy_mdec_encoder.argtypes = [C.POINTER(pb.MdecEncoder)]
+    lib.psx_audio_xa_encode.restype = C.c_int
+    lib.psx_audio_xa_encode.argtypes = [settings_cls, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    assert lib.init_mdec_encoder(C.byref(enc), 0, w, h)
+    enc.state.frame_block_base_overflow = 150 * video_per_block * 1      # (75 * speed) * video sectors * fps_den
+    enc.state.frame_block_overflow_den = interleave * 15
+    frame_buf = np.zeros(2016 * 9, np.uint8)
+    enc.state.frame_output = frame_buf.ctypes.data_as(C.POINTER(C.c_uint8))
+    enc.state.frame_index = 0
+    enc.state.frame_data_offset = 0
+    enc.state.frame_max_size = 0
+    enc.state.frame_block_overflow_num = 0
+    enc.state.quant_scale_sum = 0
+    audio_state = pb.EncoderState()
+    out = np.zeros((n_sectors, 2352), np.uint8)
+    frame_pos, sample_pos = 0, 0
+    for s in range(n_sectors):
+        if s % interleave > 0:       # video sector (filefmt.c:458-461)
+            frame_pos += lib.encode_sector_str(C.byref(enc), pb.FORMAT_STRCD, 0x8001, frames[frame_pos:].ctypes.data,
+                                               out[s].ctypes.data)
+        else:
+            n = lib.psx_audio_xa_encode(xa, C.addressof(audio_state), pcm[sample_pos:].ctypes.data, per_sector, s,
+                                        out[s].ctypes.data)
+            assert n == 2352
+            sample_pos += per_sector
+    qsum = enc.state.quant_scale_sum
+    lib.destroy_mdec_encoder(C.byref(enc))
+    return out, frame_pos, qsum
+
+
+@pytest.mark.gpu
+def test_strcd_mux_through_dropin_symbols(reference, monkeypatch):
+    """BASELINE config `strcd`: 320x240 v2 video with budgets 16128,18144,18144,... interleaved with
+    37800 Hz 4-bit stereo XA, muxed by the same loop through our symbols and the reference's."""
+    import psxavenc_b200 as pb
+    monkeypatch.setenv("PSXB200_FDCT", "sse2")      # the reference build here runs ff_fdct_sse2
+    w, h, n_sectors = 320, 240, 64
+    frames = synth.gen_frames(0, 8, w, h, 3)
+    pcm = synth.gen_pcm(2016 * 9, 2, 77)
+    ours, used_a, q_a = _mux_strcd(pb.lib(), frames, pcm, n_sectors, w, h)
+    theirs, used_b, q_b = _mux_strcd(reference.lib, frames, pcm, n_sectors, w, h)
+    assert used_a == used_b == 7 and q_a == q_b
+    assert np.array_equal(ours, theirs)
+    assert ours[1, 0x18:0x1A].tobytes() == b"\x60\x01"      # STR header where FORMAT_STRCD puts it
