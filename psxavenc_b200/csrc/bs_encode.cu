@@ -103,27 +103,29 @@ __device__ __forceinline__ int byte_of(uint32_t w, int k) { return (int)((w >> (
 template <int VARIANT>
 __global__ void __launch_bounds__(BS_DCT_THREADS, BS_DCT_MIN_CTAS)
 bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_frames, int width, int height,
-              int mbh, int nblk, int ngroups, uint4 *__restrict__ coefs, size_t frame_stride_u4) {
+              int mbh, int nmb, int cpad, int ngroups, uint4 *__restrict__ coefs, size_t frame_stride_u4) {
 	long gid = (long)blockIdx.x * BS_DCT_THREADS + threadIdx.x;
 	int lanes_per_frame = ngroups * 32;
 	int f = (int)(gid / lanes_per_frame);
-	int b = (int)(gid - (long)f * lanes_per_frame);
-	// whole warps map to one group of 32 blocks; lanes past the last block idle but stay for
+	int b = (int)(gid - (long)f * lanes_per_frame);   // plane index (type-major, see BsGeometry)
+	// whole warps map to one group of 32 blocks of one kind; padding lanes idle but stay for
 	// the warp reductions below
-	const bool active = f < n_frames && b < nblk;
+	const bool chroma = b < cpad;   // warp-uniform: cpad is a multiple of 32
+	const bool active = f < n_frames && (chroma ? b < 2 * nmb : b - cpad < 4 * nmb);
 
 	uint32_t sign_lo = 0, sign_hi = 0;
 	uint32_t rowq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	uint4 *dst = coefs + (size_t)f * frame_stride_u4 + (size_t)(b >> 5) * (BS_U4_PER_BLOCK * 32) + (b & 31);
 
 	if (active) {
-		// bitstream order: macroblock columns outermost, rows next, then Cr Cb Y1 Y2 Y3 Y4
-		int mb = b / 6, k = b - 6 * mb;
+		// macroblocks in bitstream order: columns outermost, rows next (mdec.c:689-704)
+		int mb = chroma ? b >> 1 : (b - cpad) >> 2;
+		int k = chroma ? b & 1 : 2 + ((b - cpad) & 3);
 		int mx = mb / mbh, my = mb - mx * mbh;
 		const uint8_t *fr = frames + (size_t)f * frame_bytes;
 
 		int v[64];
-		if (k < 2) {
+		if (chroma) {
 			// interleaved CrCb plane: Cr at even bytes, Cb at odd (mdec.c:627-628)
 			const uint8_t *p = fr + (size_t)width * height + (size_t)width * (my * 8) + mx * 16;
 #pragma unroll
@@ -434,14 +436,15 @@ __device__ __forceinline__ int quant_dc(uint32_t mag, uint32_t negative) {
 
 template <bool V3, bool SMEM_STREAM, int MAX_THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS)
-bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk, int ngroups, int nmb, int codec,
+bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk, int ngroups, int nsgroups, int cpad,
+               int nmb, int codec,
                const int *__restrict__ max_sizes, int max_size_bound, uint8_t *__restrict__ out, size_t out_stride,
                psxb200_bs_result_t *__restrict__ results, uint32_t *__restrict__ gstream, size_t gstream_stride,
                const BsStrLayout str) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
 	const int f = blockIdx.x;
-	const int padded = ngroups * 32;
+	const int padded = nsgroups * 32;   // blocks in bitstream order, rounded up to whole scan groups
 	const int stream_words = (max_size_bound + 3) / 4 + 2;
 
 	// fixed-size tables first so that their shared-memory addresses are compile-time offsets
@@ -455,7 +458,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		s.qpar = reinterpret_cast<uint2 *>(take(8 * 2 * 64));
 		s.stream = reinterpret_cast<uint32_t *>(SMEM_STREAM ? take(4 * (size_t)stream_words) : p);
 		s.dctab = reinterpret_cast<uint32_t *>(V3 ? take(4 * 1024) : p);
-		s.gtot = reinterpret_cast<uint32_t *>(take(4 * (size_t)(ngroups + 1)));
+		s.gtot = reinterpret_cast<uint32_t *>(take(4 * (size_t)(nsgroups + 1)));
 		s.rowq = reinterpret_cast<uint2 *>(take(8 * (size_t)ngroups));
 		s.lens = reinterpret_cast<uint16_t *>(take(2 * (size_t)padded));
 		s.dcval = reinterpret_cast<int16_t *>(V3 ? take(2 * (size_t)padded) : p);
@@ -479,14 +482,17 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	if (V3) for (int i = tid; i < 1024; i += T) s.dctab[i] = c_dcvlc[i];
 	for (int i = tid; i < words; i += T) stream[i] = 0;
 	if (tid < 8) s.misc[tid] = 0;
+	for (int b = nblk + tid; b < padded; b += T) s.lens[b] = 0;   // scan padding
 	for (int i = tid; i < 64; i += T) s.qpar[64 + i] = c_qparam[64 + i];   // q = 1
 	for (int g = tid; g < ngroups; g += T) {
 		uint4 r8 = fc[(size_t)g * (BS_U4_PER_BLOCK * 32) + 8 * 32];   // lane 0's sign row carries the group's rowq
 		s.rowq[g] = make_uint2(r8.z, r8.w);
 	}
 	if (V3) {
-		for (int b = tid; b < nblk; b += T) {
-			const uint4 *gp = fc + (size_t)(b >> 5) * (BS_U4_PER_BLOCK * 32) + (b & 31);
+		for (int pi = tid; pi < ngroups * 32; pi += T) {
+			int b = bs_plane_to_block(pi, cpad, nmb);
+			if (b < 0) continue;
+			const uint4 *gp = fc + (size_t)(pi >> 5) * (BS_U4_PER_BLOCK * 32) + (pi & 31);
 			uint32_t w0 = reinterpret_cast<const uint32_t *>(gp)[0];
 			uint32_t sg = reinterpret_cast<const uint32_t *>(gp + 8 * 32)[0];
 			s.dcval[b] = (int16_t)quant_dc(w0 & 0xFFFFu, sg & 1u);
@@ -507,15 +513,14 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 			for (int i = tid; i < 64; i += T) s.qpar[((q + 1) & 1) * 64 + i] = c_qparam[(q + 1) * 64 + i];
 		const uint2 *qpar = s.qpar + (q & 1) * 64;
 		for (int g = wid; g < ngroups; g += nw) {
-			int b = g * 32 + lane;
-			int bits = 0;
+			const int b = bs_plane_to_block(g * 32 + lane, cpad, nmb);
 			const int prefix = live_prefix(s.rowq[g], q);
-			if (b < nblk) {
-				bits = ac_bits(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane, qpar, c_qparam + q * 64, s.lenlut, prefix);
+			if (b >= 0) {
+				int bits = ac_bits(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane, qpar, c_qparam + q * 64, s.lenlut, prefix);
 				bits += 2 + (V3 ? (int)(dc_code(b) >> 24) : 10);
+				s.lens[b] = (uint16_t)bits;
+				mine += bits;
 			}
-			s.lens[b] = (uint16_t)bits;
-			mine += bits;
 		}
 		mine = warp_sum(mine);
 		if (lane == 0) atomicAdd(&s.misc[q % 3], mine);
@@ -563,7 +568,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	}
 
 	// ---- (2) exclusive scan of block bit lengths in bitstream order ---------------------
-	for (int g = wid; g < ngroups; g += nw) {
+	for (int g = wid; g < nsgroups; g += nw) {
 		uint32_t v = s.lens[g * 32 + lane], inc = v;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
@@ -576,15 +581,15 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	__syncthreads();
 	if (wid == 0) {
 		uint32_t carry = 0;
-		for (int g0 = 0; g0 < ngroups; g0 += 32) {
+		for (int g0 = 0; g0 < nsgroups; g0 += 32) {
 			int g = g0 + lane;
-			uint32_t v = g < ngroups ? s.gtot[g] : 0, inc = v;
+			uint32_t v = g < nsgroups ? s.gtot[g] : 0, inc = v;
 #pragma unroll
 			for (int d = 1; d < 32; d <<= 1) {
 				uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, d);
 				if (lane >= d) inc += u;
 			}
-			if (g < ngroups) s.gtot[g] = carry + inc - v;
+			if (g < nsgroups) s.gtot[g] = carry + inc - v;
 			carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
 		}
 	}
@@ -599,15 +604,15 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		uint8_t *lev = s.lev + tid;
 		uint32_t nnz = 0;
 		for (int g = wid; g < ngroups; g += nw) {
-			int b = g * 32 + lane;
-			if (b >= nblk) continue;
+			const int b = bs_plane_to_block(g * 32 + lane, cpad, nmb);
+			if (b < 0) continue;
 			const uint4 *gp = fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane;
 			uint32_t nz_lo, nz_hi;
 			const uint32_t dc_mag = reinterpret_cast<const uint32_t *>(gp)[0] & 0xFFFFu;
 			stage_levels(gp, qpar, c_qparam + q * 64, lev, lev_stride, live_prefix(s.rowq[g], q), nz_lo, nz_hi);
 			uint4 sg = gp[8 * 32];
 			BitWriter bw;
-			bw.begin(stream, s.gtot[g] + s.lens[b]);
+			bw.begin(stream, s.gtot[b >> 5] + s.lens[b]);
 			if (V3) {
 				uint32_t e = dc_code(b);
 				bw.put((int)(e >> 24), e & 0xFFFFFFu);
@@ -679,8 +684,9 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 
 // ---- launchers ---------------------------------------------------------------------------
 
-size_t bs_pack_smem_bytes(bool v3, bool smem_stream, int ngroups, int max_size_bound, int threads) {
-	size_t padded = (size_t)ngroups * 32;
+size_t bs_pack_smem_bytes(bool v3, bool smem_stream, const BsGeometry &geo, int max_size_bound, int threads) {
+	const int ngroups = geo.ngroups;
+	size_t padded = (size_t)geo.nsgroups * 32;
 	size_t n = 0;
 	auto take = [&](size_t bytes) { n += (bytes + 15) & ~(size_t)15; };
 	take(64 * 64);                        // lenlut
@@ -689,7 +695,7 @@ size_t bs_pack_smem_bytes(bool v3, bool smem_stream, int ngroups, int max_size_b
 	take(8 * 2 * 64);                     // qpar
 	if (smem_stream) take(4 * (size_t)((max_size_bound + 3) / 4 + 2));
 	if (v3) take(4 * 1024);               // dctab
-	take(4 * (size_t)(ngroups + 1));      // gtot
+	take(4 * (size_t)(geo.nsgroups + 1)); // gtot
 	take(8 * (size_t)ngroups);            // rowq
 	take(2 * padded);                     // lens
 	if (v3) take(2 * padded);             // dcval
@@ -703,10 +709,12 @@ cudaError_t bs_launch_dct(int fdct_variant, const uint8_t *d_frames, size_t fram
 	unsigned grid = (unsigned)((lanes + BS_DCT_THREADS - 1) / BS_DCT_THREADS);
 	if (fdct_variant == FDCT_SSE2)
 		bs_dct_kernel<FDCT_SSE2><<<grid, BS_DCT_THREADS, 0, stream>>>(d_frames, frame_bytes, n, width, height, geo.mbh,
-		                                                              geo.nblk, geo.ngroups, d_coefs, geo.frame_stride_u4);
+		                                                              geo.nmb, geo.cgroups * 32, geo.ngroups, d_coefs,
+		                                                              geo.frame_stride_u4);
 	else
 		bs_dct_kernel<FDCT_ISLOW><<<grid, BS_DCT_THREADS, 0, stream>>>(d_frames, frame_bytes, n, width, height, geo.mbh,
-		                                                               geo.nblk, geo.ngroups, d_coefs, geo.frame_stride_u4);
+		                                                               geo.nmb, geo.cgroups * 32, geo.ngroups, d_coefs,
+		                                                               geo.frame_stride_u4);
 	return cudaGetLastError();
 }
 
@@ -722,7 +730,8 @@ static cudaError_t launch_pack_t(int threads, size_t smem, int n, const uint4 *d
 		if (e != cudaSuccess) return e;
 		configured = smem;
 	}
-	kern<<<n, threads, smem, stream>>>(d_coefs, geo.frame_stride_u4, geo.nblk, geo.ngroups, geo.mbw * geo.mbh, codec,
+	kern<<<n, threads, smem, stream>>>(d_coefs, geo.frame_stride_u4, geo.nblk, geo.ngroups, geo.nsgroups,
+	                                   geo.cgroups * 32, geo.nmb, codec,
 	                                   d_max_sizes, max_size_bound, d_out, out_stride, d_results, d_gstream,
 	                                   gstream_stride, str);
 	return cudaGetLastError();
@@ -750,7 +759,7 @@ cudaError_t bs_launch_pack(int codec, int threads, int min_ctas, int n, const ui
                            const BsStrLayout &str, cudaStream_t stream) {
 	bool v3 = codec != 0;
 	bool smem_stream = d_gstream == nullptr;
-	size_t smem = bs_pack_smem_bytes(v3, smem_stream, geo.ngroups, max_size_bound, threads);
+	size_t smem = bs_pack_smem_bytes(v3, smem_stream, geo, max_size_bound, threads);
 #define PSXB200_CFG_ARGS v3, smem_stream, threads, smem, n, d_coefs, geo, codec, d_max_sizes, max_size_bound, d_out, \
 	out_stride, d_results, d_gstream, gstream_stride, str, stream
 	// register budget variants: (max threads per CTA, CTAs per SM the register file must hold)

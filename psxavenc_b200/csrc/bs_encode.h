@@ -21,17 +21,39 @@ constexpr int BS_U4_PER_BLOCK = 9;
 // global memory
 constexpr size_t BS_SMEM_BUDGET = 200 * 1024;
 
+// The coefficient plane of a frame holds its blocks type-major: first the chroma blocks
+// (plane index 2*mb + k, k = 0 Cr / 1 Cb), padded to a whole group of 32, then the luma blocks
+// (cpad + 4*mb + y, y = 0..3 for Y1..Y4); mb counts macroblocks in bitstream order (columns
+// outermost, mdec.c:689-704). Every group of 32 lanes is thus of one kind: the FDCT kernel's
+// gather does not diverge and the pack kernel's dead-row skipping follows the (usually much
+// smoother) chroma separately from the luma.
 struct BsGeometry {
 	int mbw, mbh;            // macroblocks per row / column
-	int nblk;                // 8x8 blocks per frame = 6 * mbw * mbh
-	int ngroups;             // ceil(nblk / 32)
+	int nmb;                 // macroblocks per frame
+	int nblk;                // 8x8 blocks per frame = 6 * nmb
+	int cgroups;             // plane groups holding chroma = ceil(2 * nmb / 32)
+	int ngroups;             // plane groups per frame = cgroups + ceil(4 * nmb / 32)
+	int nsgroups;            // groups of 32 blocks in bitstream order = ceil(nblk / 32)
 	size_t frame_stride_u4;  // coefficient plane stride between frames, in uint4
 
 	BsGeometry(int width, int height)
-		: mbw(width / 16), mbh(height / 16), nblk(6 * (width / 16) * (height / 16)),
-		  ngroups((6 * (width / 16) * (height / 16) + 31) / 32),
-		  frame_stride_u4((size_t)((6 * (width / 16) * (height / 16) + 31) / 32) * BS_U4_PER_BLOCK * 32) {}
+		: mbw(width / 16), mbh(height / 16), nmb(mbw * mbh), nblk(6 * nmb), cgroups((2 * nmb + 31) / 32),
+		  ngroups(cgroups + (4 * nmb + 31) / 32), nsgroups((nblk + 31) / 32),
+		  frame_stride_u4((size_t)ngroups * BS_U4_PER_BLOCK * 32) {}
 };
+
+// Bitstream-order block index (6*mb + k, k = Cr Cb Y1 Y2 Y3 Y4) of plane index pi, -1 for padding.
+__host__ __device__ inline int bs_plane_to_block(int pi, int cpad, int nmb) {
+	if (pi < cpad) return pi < 2 * nmb ? 6 * (pi >> 1) + (pi & 1) : -1;
+	int li = pi - cpad;
+	return li < 4 * nmb ? 6 * (li >> 2) + 2 + (li & 3) : -1;
+}
+
+// Plane index of bitstream-order block b.
+__host__ __device__ inline int bs_block_to_plane(int b, int cpad) {
+	int mb = b / 6, k = b - 6 * mb;
+	return k < 2 ? 2 * mb + k : cpad + 4 * mb + (k - 2);
+}
 
 // STR sector output mode of the pack kernel (encode_sector_str, mdec.c:757-836, driven as
 // encode_file_strspu does for a video-only stream, filefmt.c:546-630). sector_size == 0: off.
@@ -49,7 +71,7 @@ struct BsStrLayout {
 };
 
 void bs_upload_tables();
-size_t bs_pack_smem_bytes(bool v3, bool smem_stream, int ngroups, int max_size_bound, int threads);
+size_t bs_pack_smem_bytes(bool v3, bool smem_stream, const BsGeometry &geo, int max_size_bound, int threads);
 
 // Row stride (bytes) of the per-thread level staging columns: threads rounded so that the
 // stride in 32-bit words is odd, which spreads a warp's scattered byte reads over the banks.

@@ -174,7 +174,7 @@ static int bs_encode_chunked(psxb200_bs_encoder *enc, uint4 *d_coefs, int n, con
                              psxb200_bs_result_t *d_results, cudaStream_t stream, const BsStrLayout *str_batch = nullptr) {
 	uint32_t *gstream = nullptr;
 	size_t gstride = 0;
-	if (bs_pack_smem_bytes(enc->codec != 0, true, enc->geo.ngroups, max_size_bound, enc->pack_threads) > BS_SMEM_BUDGET) {
+	if (bs_pack_smem_bytes(enc->codec != 0, true, enc->geo, max_size_bound, enc->pack_threads) > BS_SMEM_BUDGET) {
 		gstride = (size_t)(max_size_bound + 3) / 4 + 2;
 		CU_TRY(enc->gstream.reserve(gstride * enc->max_batch));
 		gstream = enc->gstream.ptr;
