@@ -158,7 +158,7 @@ def run_reference(args):
         total += dt
     value = n * args.steps / total
     sample = "%d of the %d frames of a step per step, %d threads" % (n, FRAMES_PER_STEP, cpu.cores)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
@@ -166,7 +166,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ---------------------------------------------------------------------------------------
@@ -382,7 +382,7 @@ def run_ours(args):
                 raise SystemExit("bench.py: GPU output differs from the CPU baseline's output")
             base["parity_frames_checked"] = k
             line["cpu_baseline"] = base
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -457,6 +457,25 @@ def bench_adpcm(pb, torch, dev, stream, rank, world, dist, args):
     return result
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The driver reads ONE JSON line from stdout. Libraries underneath (NCCL's version banner,
+    anything printf'ing from C) write to file descriptor 1 as well, so fd 1 is pointed at stderr
+    for the whole run and the JSON line alone goes to the original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -472,6 +491,7 @@ def main():
     ap.add_argument("--noise", type=int, default=NOISE_BITS, help="noise_bits of the synthetic strv frames (0 easy, 3 typical, 6 hard)")
     args = ap.parse_args()
     select_workload(args.workload, args.noise)
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

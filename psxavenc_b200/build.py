@@ -36,5 +36,16 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(path, defines):
+    """A/B builds for tools/ab.sh: the same sources with extra -D switches, written to `path`
+    (loaded through PSXB200_LIB=...). Not used by the product."""
+    cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + ["-o", path] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.run(cmd, check=True)
+    return path
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

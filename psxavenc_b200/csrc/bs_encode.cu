@@ -208,7 +208,7 @@ struct PackSmem {
 	uint32_t *gtot;     // per group bit totals -> exclusive group bases
 	uint2 *qpar;        // [2][64] copies of c_qparam rows: [q & 1] holds the current q's
 	uint2 *rowq;        // per group: last live quant scale of each plane row (8 bytes, from bs_dct_kernel)
-	uint32_t *misc;     // [0..2] rotating frame totals, [3] nonzero AC count, [4..] scan scratch
+	uint32_t *misc;     // [0..2] rotating frame totals, [3] nonzero AC count, [8..] scan scratch
 	uint32_t *vlc;      // [min(level,63)][run] -> (len<<24)|code, see g_vlc
 	uint16_t *lens;     // per block bit length at the current q; after the scan: exclusive offset in its group
 	int16_t *dcval;     // v3: per block quantised DC, replaced in place by its coded delta
@@ -504,28 +504,37 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	auto dc_code = [&](int b) { return s.dctab[((b % 6) < 2 ? 0 : 512) + (s.dcval[b] & 0x1FF)]; };
 
 	// ---- (1) first-fit quant scale search ------------------------------------------------
+	// Largest bit total (blocks only) that still fits: 8 + 2*ceil((bits + 10)/16) <= max_size. A
+	// pass whose running total passes it has failed (the reference's writer overflows at that
+	// point too, mdec.c:323-325) and is abandoned early.
+	const int limit_bits = max_size >= 8 ? 16 * ((max_size - 8) >> 1) - 10 : -1;
 	int q = 1;
 	uint32_t total_bits = 0;
 	for (; q < 64; q++) {
-		uint32_t mine = 0;
 		// next pass's reciprocals; readers only touch them after this pass's closing barrier
 		if (q < 63)
 			for (int i = tid; i < 64; i += T) s.qpar[((q + 1) & 1) * 64 + i] = c_qparam[(q + 1) * 64 + i];
 		const uint2 *qpar = s.qpar + (q & 1) * 64;
-		for (int g = wid; g < ngroups; g += nw) {
+		// the (usually busier) luma groups at the high end of the plane go first; drawing groups
+		// from a shared ticket counter instead of this static round-robin measured no better
+		uint32_t *total = &s.misc[q % 3];
+		for (int g = ngroups - 1 - wid; g >= 0; g -= nw) {
 			const int b = bs_plane_to_block(g * 32 + lane, cpad, nmb);
 			const int prefix = live_prefix(s.rowq[g], q);
+			int bits = 0;
 			if (b >= 0) {
-				int bits = ac_bits(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane, qpar, c_qparam + q * 64, s.lenlut, prefix);
+				bits = ac_bits(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane, qpar, c_qparam + q * 64, s.lenlut, prefix);
 				bits += 2 + (V3 ? (int)(dc_code(b) >> 24) : 10);
 				s.lens[b] = (uint16_t)bits;
-				mine += bits;
 			}
+			const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)bits);
+			uint32_t before = 0;
+			if (lane == 0) before = atomicAdd(total, sum);
+			before = __shfl_sync(0xFFFFFFFFu, before, 0);
+			if ((int)(before + sum) > limit_bits) break;
 		}
-		mine = warp_sum(mine);
-		if (lane == 0) atomicAdd(&s.misc[q % 3], mine);
 		__syncthreads();
-		total_bits = s.misc[q % 3];
+		total_bits = *total;
 		if (tid == 0) s.misc[(q + 2) % 3] = 0;
 		// stream = blocks + 10-bit end-of-frame code; byte budget rule of flush_bits
 		int units = (int)((total_bits + 10 + 15) >> 4);
@@ -603,7 +612,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		const uint2 *qpar = s.qpar + (q & 1) * 64;
 		uint8_t *lev = s.lev + tid;
 		uint32_t nnz = 0;
-		for (int g = wid; g < ngroups; g += nw) {
+		for (int g = ngroups - 1 - wid; g >= 0; g -= nw) {
 			const int b = bs_plane_to_block(g * 32 + lane, cpad, nmb);
 			if (b < 0) continue;
 			const uint4 *gp = fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane;
