@@ -52,20 +52,34 @@ __device__ __forceinline__ void encode_unit(const int (&s)[UNIT], int qerr, int 
 	const bool has_candidate = filter < FILTERS;
 	const int k1 = filter_k1(has_candidate ? filter : 0), k2 = filter_k2(has_candidate ? filter : 0);
 
-	// find_min_shift (adpcm.c:39-79): open-loop residual range over the raw samples
+	// find_min_shift (adpcm.c:39-79): open-loop residual range over the raw samples. The range
+	// does not depend on the shift, so the three shift candidates of a filter scan a third of
+	// the unit each (samples 0-9, 10-18, 19-27) and combine the bit lengths of their extremes.
 	int lo = 0, hi = 0;
 	{
-		int q1 = p1, q2 = p2;
+		// branch-free three-way selects (masks), so that the compiler keeps one copy of the code
+		const int m0 = -(which == 0), m1 = -(which == 1), m2 = -(which == 2);
+		int q1 = (p1 & m0) | (s[9] & m1) | (s[18] & m2);
+		int q2 = (p2 & m0) | (s[8] & m1) | (s[17] & m2);
 #pragma unroll
-		for (int i = 0; i < UNIT; i++) {
-			int r = s[i] - ((k1 * q1 + k2 * q2 + 32) >> 6);
+		for (int j = 0; j < 10; j++) {
+			const int x = (s[j] & m0) | (s[j < 9 ? j + 10 : 18] & m1) | (s[j < 9 ? j + 19 : 27] & m2);
+			int r = x - ((k1 * q1 + k2 * q2 + 32) >> 6);
+			if (j == 9) r &= m0;   // the second and third parts are 9 samples long
 			lo = min(lo, r);
 			hi = max(hi, r);
 			q2 = q1;
-			q1 = s[i];
+			q1 = x;
 		}
 	}
-	int rs = max(bit_length((uint32_t)hi), bit_length((uint32_t)max(~lo, 0))) - KEEP;
+	int bl = max(bit_length((uint32_t)hi), bit_length((uint32_t)max(~lo, 0)));
+	{
+		const int first = sub - which;   // lanes first..first+2 hold this filter
+		const int b1 = __shfl_sync(0xFFFFFFFFu, bl, first + which + 1 - 3 * (which == 2), 16);   // (which + 1) % 3
+		const int b2 = __shfl_sync(0xFFFFFFFFu, bl, first + which + 2 - 3 * (which != 0), 16);   // (which + 2) % 3
+		bl = max(bl, max(b1, b2));
+	}
+	int rs = bl - KEEP;
 	rs = min(max(rs, 0), RANGE);
 	const int shift = RANGE - rs + which - 1;    // candidates m-1, m, m+1 (adpcm.c:161-167)
 	const bool valid = has_candidate && shift >= 0 && shift <= RANGE;
@@ -76,15 +90,19 @@ __device__ __forceinline__ void encode_unit(const int (&s)[UNIT], int qerr, int 
 	unsigned long long err2 = 0;
 #pragma unroll
 	for (int j = 0; j < (RANGE == 12 ? 4 : 7); j++) codes[j] = 0;
+	// ((x << sh) + 2^(RANGE-1)) >> RANGE == (x + (2^(RANGE-1) >> sh)) >> (RANGE - sh) for 0 <= sh <= RANGE
+	// (floor division by a power of two; nothing overflows: |x| < 2^17), which takes the left
+	// shift off the serial chain; qerr rides along in the rounding term.
+	const int down = RANGE - sh;
+	const int round_q = ((1 << (RANGE - 1)) >> sh) + qerr;
 #pragma unroll
 	for (int i = 0; i < UNIT; i++) {
-		int want = s[i] + qerr;
 		int pred = (k1 * t1 + k2 * t2 + 32) >> 6;
-		int e = (((want - pred) << sh) + (1 << (RANGE - 1))) >> RANGE;
+		int e = (s[i] - pred + round_q) >> down;
 		e = min(max(e, LO), HI);
-		int dec = (e << (RANGE - sh)) + pred;
+		int dec = (e << down) + pred;
 		dec = min(max(dec, -0x8000), 0x7FFF);
-		int d = dec - want;
+		int d = dec - s[i] - qerr;
 		err2 += (unsigned long long)((long long)d * d);
 		codes[(i * BITS) >> 5] |= ((uint32_t)e & MASK) << ((i * BITS) & 31);
 		t2 = t1;

@@ -103,15 +103,16 @@ __device__ __forceinline__ int byte_of(uint32_t w, int k) { return (int)((w >> (
 template <int VARIANT>
 __global__ void __launch_bounds__(BS_DCT_THREADS, BS_DCT_MIN_CTAS)
 bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_frames, int width, int height,
-              int mbh, int nmb, int cpad, int ngroups, uint4 *__restrict__ coefs, size_t frame_stride_u4) {
-	long gid = (long)blockIdx.x * BS_DCT_THREADS + threadIdx.x;
-	int lanes_per_frame = ngroups * 32;
-	int f = (int)(gid / lanes_per_frame);
-	int b = (int)(gid - (long)f * lanes_per_frame);   // plane index (type-major, see BsGeometry)
+              int mbh, uint32_t mbh_magic, int nmb, int cpad, int ngroups, uint4 *__restrict__ coefs,
+              size_t frame_stride_u4) {
+	// grid: x = chunk of 128 plane lanes within the frame, y = frame
+	const int f = blockIdx.y;
+	const int b = blockIdx.x * BS_DCT_THREADS + threadIdx.x;   // plane index (type-major, see BsGeometry)
+	if (b >= ngroups * 32) return;                             // whole warps: ngroups * 32 lanes per frame
 	// whole warps map to one group of 32 blocks of one kind; padding lanes idle but stay for
 	// the warp reductions below
 	const bool chroma = b < cpad;   // warp-uniform: cpad is a multiple of 32
-	const bool active = f < n_frames && (chroma ? b < 2 * nmb : b - cpad < 4 * nmb);
+	const bool active = chroma ? b < 2 * nmb : b - cpad < 4 * nmb;
 
 	uint32_t sign_lo = 0, sign_hi = 0;
 	uint32_t rowq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -121,7 +122,7 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
 		// macroblocks in bitstream order: columns outermost, rows next (mdec.c:689-704)
 		int mb = chroma ? b >> 1 : (b - cpad) >> 2;
 		int k = chroma ? b & 1 : 2 + ((b - cpad) & 3);
-		int mx = mb / mbh, my = mb - mx * mbh;
+		int mx = (int)__umulhi((uint32_t)mb, mbh_magic), my = mb - mx * mbh;   // mb / mbh
 		const uint8_t *fr = frames + (size_t)f * frame_bytes;
 
 		int v[64];
@@ -159,19 +160,26 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
 		fdct8x8<VARIANT>(v);
 		v[0] -= 8192;
 
+		// Coefficients are visited in descending zig-zag order so that each sign can be shifted
+		// into its mask with one funnel shift and coefficient i ends up at bit i of its half.
 #pragma unroll
-		for (int j = 0; j < 8; j++) {
+		for (int j = 7; j >= 0; j--) {
 			uint32_t w[4];
 			uint32_t rowmax = 0;
 #pragma unroll
-			for (int t = 0; t < 4; t++) {
+			for (int t = 3; t >= 0; t--) {
 				int i0 = 8 * j + 2 * t;
 				int c0 = v[zigzag_at(i0)], c1 = v[zigzag_at(i0 + 1)];
 				uint32_t m0 = (uint32_t)abs(c0), m1 = (uint32_t)abs(c1);
 				w[t] = m0 | (m1 << 16);
 				rowmax = max(rowmax, i0 == 0 ? m1 : max(m0, m1));   // the DC term has its own fixed step
-				uint32_t sg = ((uint32_t)c0 >> 31) | (((uint32_t)c1 >> 31) << 1);
-				if (i0 < 32) sign_lo |= sg << i0; else sign_hi |= sg << (i0 - 32);
+				if (i0 < 32) {
+					sign_lo = __funnelshift_l((uint32_t)c1, sign_lo, 1);
+					sign_lo = __funnelshift_l((uint32_t)c0, sign_lo, 1);
+				} else {
+					sign_hi = __funnelshift_l((uint32_t)c1, sign_hi, 1);
+					sign_hi = __funnelshift_l((uint32_t)c0, sign_hi, 1);
+				}
 			}
 			dst[j * 32] = make_uint4(w[0], w[1], w[2], w[3]);
 			// A coefficient quantises to nonzero at scale q iff 2*|c| >= quant*q, so nothing in
@@ -192,7 +200,7 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
 	}
 	if (active) {
 		dst[8 * 32] = make_uint4(sign_lo, sign_hi, packed_lo, packed_hi);
-	} else if (f < n_frames) {
+	} else {
 		// padding lanes of the last group: keep the plane fully defined (the pack kernel lets
 		// them run along so that its warps stay convergent)
 #pragma unroll
@@ -714,16 +722,22 @@ size_t bs_pack_smem_bytes(bool v3, bool smem_stream, const BsGeometry &geo, int 
 
 cudaError_t bs_launch_dct(int fdct_variant, const uint8_t *d_frames, size_t frame_bytes, int n, int width, int height,
                           const BsGeometry &geo, uint4 *d_coefs, cudaStream_t stream) {
-	long lanes = (long)n * geo.ngroups * 32;
-	unsigned grid = (unsigned)((lanes + BS_DCT_THREADS - 1) / BS_DCT_THREADS);
-	if (fdct_variant == FDCT_SSE2)
-		bs_dct_kernel<FDCT_SSE2><<<grid, BS_DCT_THREADS, 0, stream>>>(d_frames, frame_bytes, n, width, height, geo.mbh,
-		                                                              geo.nmb, geo.cgroups * 32, geo.ngroups, d_coefs,
-		                                                              geo.frame_stride_u4);
-	else
-		bs_dct_kernel<FDCT_ISLOW><<<grid, BS_DCT_THREADS, 0, stream>>>(d_frames, frame_bytes, n, width, height, geo.mbh,
-		                                                               geo.nmb, geo.cgroups * 32, geo.ngroups, d_coefs,
-		                                                               geo.frame_stride_u4);
+	const unsigned per_frame = (unsigned)((geo.ngroups * 32 + BS_DCT_THREADS - 1) / BS_DCT_THREADS);
+	const uint32_t mbh_magic = (uint32_t)(0x100000000ull / (unsigned)geo.mbh) + 1;   // exact mb / mbh for mb < 2^16
+	for (int first = 0; first < n; first += 65535) {   // gridDim.y limit
+		const int m = n - first < 65535 ? n - first : 65535;
+		const dim3 grid(per_frame, (unsigned)m);
+		const uint8_t *src = d_frames + (size_t)first * frame_bytes;
+		uint4 *dst = d_coefs + (size_t)first * geo.frame_stride_u4;
+		if (fdct_variant == FDCT_SSE2)
+			bs_dct_kernel<FDCT_SSE2><<<grid, BS_DCT_THREADS, 0, stream>>>(src, frame_bytes, m, width, height, geo.mbh, mbh_magic,
+			                                                              geo.nmb, geo.cgroups * 32, geo.ngroups, dst,
+			                                                              geo.frame_stride_u4);
+		else
+			bs_dct_kernel<FDCT_ISLOW><<<grid, BS_DCT_THREADS, 0, stream>>>(src, frame_bytes, m, width, height, geo.mbh, mbh_magic,
+			                                                               geo.nmb, geo.cgroups * 32, geo.ngroups, dst,
+			                                                               geo.frame_stride_u4);
+	}
 	return cudaGetLastError();
 }
 
