@@ -122,7 +122,7 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
 		// macroblocks in bitstream order: columns outermost, rows next (mdec.c:689-704)
 		int mb = chroma ? b >> 1 : (b - cpad) >> 2;
 		int k = chroma ? b & 1 : 2 + ((b - cpad) & 3);
-		int mx = (int)__umulhi((uint32_t)mb, mbh_magic), my = mb - mx * mbh;   // mb / mbh
+		int mx = mbh_magic ? (int)__umulhi((uint32_t)mb, mbh_magic) : mb, my = mb - mx * mbh;   // mb / mbh (magic 0: mbh == 1)
 		const uint8_t *fr = frames + (size_t)f * frame_bytes;
 
 		int v[64];
@@ -723,7 +723,8 @@ size_t bs_pack_smem_bytes(bool v3, bool smem_stream, const BsGeometry &geo, int 
 cudaError_t bs_launch_dct(int fdct_variant, const uint8_t *d_frames, size_t frame_bytes, int n, int width, int height,
                           const BsGeometry &geo, uint4 *d_coefs, cudaStream_t stream) {
 	const unsigned per_frame = (unsigned)((geo.ngroups * 32 + BS_DCT_THREADS - 1) / BS_DCT_THREADS);
-	const uint32_t mbh_magic = (uint32_t)(0x100000000ull / (unsigned)geo.mbh) + 1;   // exact mb / mbh for mb < 2^16
+	// exact mb / mbh for mb < 2^16; 0 stands for mbh == 1, whose reciprocal does not fit
+	const uint32_t mbh_magic = geo.mbh > 1 ? (uint32_t)(0x100000000ull / (unsigned)geo.mbh) + 1 : 0;
 	for (int first = 0; first < n; first += 65535) {   // gridDim.y limit
 		const int m = n - first < 65535 ? n - first : 65535;
 		const dim3 grid(per_frame, (unsigned)m);
