@@ -5,10 +5,13 @@
 //
 //   bs_dct_kernel      one thread per 8x8 block: gathers the block from the NV21 frame
 //                      (mdec.c:605-634), level-shifts, runs the bit-exact integer FDCT in
-//                      registers (mdec.c:640) and stores |coef| (u16) in zig-zag order plus a
-//                      64-bit sign mask into a coefficient plane laid out so that the 32
-//                      lanes of a warp (32 consecutive blocks in bitstream order) read and
-//                      write 512 contiguous bytes per uint4 access.
+//                      registers (mdec.c:640) and reduces every AC coefficient to
+//                      y = floor(2|c| / quant[i]), from which the level at ANY quant scale q is
+//                      (y + q) / (2q) exactly (see below). Only the coefficients with y >= 1 —
+//                      the ones that can be nonzero at some q — are kept, as a list of 16-bit
+//                      (y, zig-zag position) entries per block, plus a 64-bit sign mask and the
+//                      DC term. Lists are laid out so that the 32 lanes of a warp (32 blocks of
+//                      one kind) read and write 512 contiguous bytes per uint4 access.
 //   bs_pack_kernel     one CTA per frame, one thread per block and quant scale:
 //                      (1) first-fit quant-scale search q = 1,2,... (mdec.c:663-722): each
 //                          thread prices its blocks' run/level codes from a shared-memory
@@ -21,8 +24,12 @@
 //                      (4) header (mdec.c:725-754) and coalesced copy-out with the 16-bit
 //                          little-endian word order of the format, zero padded.
 //
-// Division by the quantiser step uses an exact 32-bit reciprocal (DIVIDE_ROUNDED,
-// mdec.c:438, is round-half-away-from-zero == (|n| + d/2) / d in integers).
+// Quantisation: DIVIDE_ROUNDED (mdec.c:438) is round-half-away-from-zero, i.e. for d = quant*q
+//   |level| = floor((2|c| + d) / 2d) = floor((floor(2|c| / quant) + q) / 2q)
+// (nested floor divisions; quant*q / quant = q is an integer). The inner division is by a
+// compile-time constant and independent of q, so it is done once in the FDCT kernel; the outer
+// one has the same divisor for all 63 AC coefficients of a pass, and a coefficient is nonzero at
+// q iff y >= q. For 8-bit input |c| <= 8192 and quant >= 16, so y < 1024 (10 bits).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -33,8 +40,9 @@
 namespace psxb200 {
 
 // ---- constant tables -------------------------------------------------------------------
-// [q][i] -> (magic, half): level = umulhi(|coef| + half, magic), d = QUANT_ZZ[i] * q.
-__constant__ uint2 c_qparam[64 * 64];
+// [q] -> reciprocals of the pass's common divisor: .x = floor(2^32 / 2q) + 1 for t = y + q,
+// .y = floor(2^32 / 128q) + 1 for t = 64 (y + q) + (any 6 low bits); level = umulhi(t, magic).
+__constant__ uint2 c_qmagic[64];
 // [min(level,63)][run] -> code length in bits incl. sign (22 = escape), 0 for level 0.
 __constant__ uint8_t c_lenlut[64 * 64];
 // [min(level,63)][run] -> (len << 24) | code with the sign bit (LSB) clear; level 0 -> 0;
@@ -53,26 +61,20 @@ __host__ __device__ constexpr int quant_zz_at(int i) {
 	return t[i];
 }
 
-// Smallest quantiser entry among the AC coefficients of plane row j (zig-zag 8j..8j+7).
-__host__ __device__ constexpr int row_min_quant(int j) {
-	int m = 255;
-	for (int i = 8 * j; i < 8 * j + 8; i++)
-		if (i > 0 && quant_zz_at(i) < m) m = quant_zz_at(i);
-	return m;
+// umulhi(|c|, ymagic_at(i)) == floor(2|c| / quant of zig-zag position i), exact for |c| < 2^15.
+__host__ __device__ constexpr uint32_t ymagic_at(int i) {
+	return (uint32_t)(0x200000000ull / (unsigned long long)quant_zz_at(i)) + 1u;
 }
 
 void bs_upload_tables() {
-	static uint2 qparam[64 * 64];
+	static uint2 qmagic[64];
 	static uint8_t lenlut[64 * 64];
 	static uint32_t vlc[64 * 64];
 	static uint32_t dcvlc[2 * 512];
 	for (int q = 0; q < 64; q++) {
-		for (int i = 0; i < 64; i++) {
-			uint32_t d = (uint32_t)BS_QUANT_ZZ[i] * (q ? q : 1);
-			if (i == 0) d = 16;
-			qparam[q * 64 + i].x = (uint32_t)(0x100000000ull / d) + 1;
-			qparam[q * 64 + i].y = d / 2;
-		}
+		uint32_t d = 2u * (q ? q : 1);
+		qmagic[q].x = (uint32_t)(0x100000000ull / d) + 1;
+		qmagic[q].y = (uint32_t)(0x100000000ull / (64ull * d)) + 1;
 	}
 	for (int lv = 0; lv < 64; lv++) {
 		for (int run = 0; run < 64; run++) {
@@ -90,7 +92,7 @@ void bs_upload_tables() {
 		dcvlc[i] = BS_DC_VLC_CHROMA[i];
 		dcvlc[512 + i] = BS_DC_VLC_LUMA[i];
 	}
-	cudaMemcpyToSymbol(c_qparam, qparam, sizeof(qparam));
+	cudaMemcpyToSymbol(c_qmagic, qmagic, sizeof(qmagic));
 	cudaMemcpyToSymbol(c_lenlut, lenlut, sizeof(lenlut));
 	cudaMemcpyToSymbol(g_vlc, vlc, sizeof(vlc));
 	cudaMemcpyToSymbol(c_dcvlc, dcvlc, sizeof(dcvlc));
@@ -105,6 +107,15 @@ __global__ void __launch_bounds__(BS_DCT_THREADS, BS_DCT_MIN_CTAS)
 bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_frames, int width, int height,
               int mbh, uint32_t mbh_magic, int nmb, int cpad, int ngroups, uint4 *__restrict__ coefs,
               size_t frame_stride_u4) {
+	// Per-thread list columns: entry k of thread t at s_list[k * BS_DCT_THREADS + t] (a warp's
+	// appends fall into distinct banks whatever the lanes' fill levels). Zeroed first so that the
+	// tail of every list reads as "no coefficient".
+	__shared__ __align__(16) uint16_t s_list[64 * BS_DCT_THREADS];
+#pragma unroll
+	for (int j = 0; j < (64 * 2) / 16; j++)
+		reinterpret_cast<uint4 *>(s_list)[threadIdx.x + BS_DCT_THREADS * j] = make_uint4(0, 0, 0, 0);
+	__syncthreads();
+
 	// grid: x = chunk of 128 plane lanes within the frame, y = frame
 	const int f = blockIdx.y;
 	const int b = blockIdx.x * BS_DCT_THREADS + threadIdx.x;   // plane index (type-major, see BsGeometry)
@@ -114,8 +125,11 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
 	const bool chroma = b < cpad;   // warp-uniform: cpad is a multiple of 32
 	const bool active = chroma ? b < 2 * nmb : b - cpad < 4 * nmb;
 
-	uint32_t sign_lo = 0, sign_hi = 0;
-	uint32_t rowq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	uint32_t sign_lo = 0, sign_hi = 0, dc_mag = 0;
+	uint16_t *const col = s_list + threadIdx.x;
+	// the append cursor as a 32-bit shared-space address: one add per bump, no generic pointers
+	const uint32_t col_addr = (uint32_t)__cvta_generic_to_shared(col);
+	uint32_t tail = col_addr;
 	uint4 *dst = coefs + (size_t)f * frame_stride_u4 + (size_t)(b >> 5) * (BS_U4_PER_BLOCK * 32) + (b & 31);
 
 	if (active) {
@@ -160,52 +174,42 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
 		fdct8x8<VARIANT>(v);
 		v[0] -= 8192;
 
-		// Coefficients are visited in descending zig-zag order so that each sign can be shifted
-		// into its mask with one funnel shift and coefficient i ends up at bit i of its half.
+		// Coefficients are visited in descending zig-zag order: each sign is shifted into its
+		// mask with one funnel shift (coefficient i ends up at bit i of its half), and the list
+		// comes out with the highest position first — the pack kernel walks it backwards.
 #pragma unroll
-		for (int j = 7; j >= 0; j--) {
-			uint32_t w[4];
-			uint32_t rowmax = 0;
-#pragma unroll
-			for (int t = 3; t >= 0; t--) {
-				int i0 = 8 * j + 2 * t;
-				int c0 = v[zigzag_at(i0)], c1 = v[zigzag_at(i0 + 1)];
-				uint32_t m0 = (uint32_t)abs(c0), m1 = (uint32_t)abs(c1);
-				w[t] = m0 | (m1 << 16);
-				rowmax = max(rowmax, i0 == 0 ? m1 : max(m0, m1));   // the DC term has its own fixed step
-				if (i0 < 32) {
-					sign_lo = __funnelshift_l((uint32_t)c1, sign_lo, 1);
-					sign_lo = __funnelshift_l((uint32_t)c0, sign_lo, 1);
-				} else {
-					sign_hi = __funnelshift_l((uint32_t)c1, sign_hi, 1);
-					sign_hi = __funnelshift_l((uint32_t)c0, sign_hi, 1);
+		for (int i = 63; i >= 0; i--) {
+			const int c = v[zigzag_at(i)];
+			if (i < 32) sign_lo = __funnelshift_l((uint32_t)c, sign_lo, 1);
+			else sign_hi = __funnelshift_l((uint32_t)c, sign_hi, 1);
+			const uint32_t mag = (uint32_t)abs(c);
+			if (i == 0) {
+				dc_mag = mag;   // the DC term has its own fixed step (mdec.c:447, 671)
+			} else {
+				const uint32_t y = __umulhi(mag, ymagic_at(i));   // floor(2|c| / quant[i])
+				if (y) {
+					asm volatile("st.shared.u16 [%0], %1;" ::"r"(tail), "h"((uint16_t)((y << 6) | (uint32_t)i)) : "memory");
+					tail += 2 * BS_DCT_THREADS;
 				}
 			}
-			dst[j * 32] = make_uint4(w[0], w[1], w[2], w[3]);
-			// A coefficient quantises to nonzero at scale q iff 2*|c| >= quant*q, so nothing in
-			// this row survives beyond q = 2*rowmax / (smallest quant of the row).
-			rowq[j] = min(63u, 2u * rowmax / (uint32_t)row_min_quant(j));
 		}
 	}
 
-	// per group and plane row: the largest quant scale at which any of the 32 blocks still has a
-	// nonzero coefficient there; the pack kernel skips rows that are dead at its q
-	uint32_t packed_lo = 0, packed_hi = 0;
+	// The group's lists are stored as rows of 8 entries per lane, as many rows as its longest
+	// list needs; shorter lists are zero padded (y = 0: never a coefficient).
+	const int count = (int)(tail - col_addr) / (2 * BS_DCT_THREADS);
+	const int longest = (int)__reduce_max_sync(0xFFFFFFFFu, (uint32_t)count);
+	const int nrows = (longest + 7) >> 3;
+	for (int r = 0; r < nrows; r++) {
+		const uint16_t *e = col + 8 * r * BS_DCT_THREADS;
+		uint32_t w[4];
 #pragma unroll
-	for (int j = 6; j >= 0; j--) rowq[j] = max(rowq[j], rowq[j + 1]);   // a live row keeps its predecessors live
-#pragma unroll
-	for (int j = 0; j < 8; j++) {
-		uint32_t m = __reduce_max_sync(0xFFFFFFFFu, rowq[j]);
-		if (j < 4) packed_lo |= m << (8 * j); else packed_hi |= m << (8 * (j - 4));
+		for (int t = 0; t < 4; t++)
+			w[t] = (uint32_t)e[(2 * t) * BS_DCT_THREADS] | ((uint32_t)e[(2 * t + 1) * BS_DCT_THREADS] << 16);
+		dst[r * 32] = make_uint4(w[0], w[1], w[2], w[3]);
 	}
-	if (active) {
-		dst[8 * 32] = make_uint4(sign_lo, sign_hi, packed_lo, packed_hi);
-	} else {
-		// padding lanes of the last group: keep the plane fully defined (the pack kernel lets
-		// them run along so that its warps stay convergent)
-#pragma unroll
-		for (int j = 0; j < 9; j++) dst[j * 32] = make_uint4(0, 0, 0, 0);
-	}
+	// meta row: signs by zig-zag position, |DC| and this block's list length, the group's longest
+	dst[BS_META_ROW * 32] = make_uint4(sign_lo, sign_hi, dc_mag | ((uint32_t)count << 16), (uint32_t)longest);
 }
 
 // ---- kernel 2: quant-scale search + bit packing ------------------------------------------
@@ -214,14 +218,13 @@ struct PackSmem {
 	uint32_t *stream;   // bitstream image, 32-bit words, first stream bit = bit 31 of word 0
 	uint32_t *dctab;    // v3: DC delta codes, [0..511] chroma, [512..1023] luma (len<<24 | code)
 	uint32_t *gtot;     // per group bit totals -> exclusive group bases
-	uint2 *qpar;        // [2][64] copies of c_qparam rows: [q & 1] holds the current q's
-	uint2 *rowq;        // per group: last live quant scale of each plane row (8 bytes, from bs_dct_kernel)
+	uint8_t *grows;     // per plane group: list rows in use (longest list of its 32 blocks, from bs_dct_kernel)
 	uint32_t *misc;     // [0..2] rotating frame totals, [3] nonzero AC count, [8..] scan scratch
 	uint32_t *vlc;      // [min(level,63)][run] -> (len<<24)|code, see g_vlc
 	uint16_t *lens;     // per block bit length at the current q; after the scan: exclusive offset in its group
 	int16_t *dcval;     // v3: per block quantised DC, replaced in place by its coded delta
-	uint8_t *lenlut;
-	uint8_t *lev;       // emit: min(level,63) of the thread's current block, [coef][thread] with stride lev_stride
+	uint8_t *lenlut;    // [min(level,63)][run] -> code length; preceded by 16 zero guard bytes (see price_entry)
+	uint32_t *stage;    // emit: up to four list rows of the thread's current block, word j at stage[j * T + tid]
 };
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
@@ -239,102 +242,87 @@ __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
 	return d;
 }
 
-// bs_dct_kernel records, per group of 32 blocks and per plane row (8 zig-zag positions), the
-// largest quant scale at which any block of the group still has a nonzero level there. Rows
-// die from the high-frequency end, so a warp only prices / stages the live prefix of rows of
-// its group at the current q; every prefix length has its own straight-line instantiation
-// (rows are fetched up to four at a time to bound the register footprint).
+// ---- pricing: the pricing half of encode_dct_block (mdec.c:482-499) over a block's list ---
+//
+// List entries hold (y << 6) | position, two per 32-bit word; a block's list is stored highest
+// position first, so it is walked from its last entry down: zero padding first, then the
+// coefficients in ascending zig-zag order. An entry is a coefficient at quant scale q iff its
+// level (y + q) / 2q is nonzero; its run is the distance to the previous such entry.
 
-// Leading plane rows to process at quant scale q, rounded up to an instantiated prefix length
-// (0, 2, 4 or 8); rowq bytes are non-increasing in the row index. The same in every lane.
-__device__ __forceinline__ int live_prefix(uint2 rowq, int q) {
-	if ((int)(rowq.y & 0xFFu) >= q) return 8;            // row 4 live
-	if ((int)((rowq.x >> 16) & 0xFFu) >= q) return 4;    // row 2 live
-	return (int)(rowq.x & 0xFFu) >= q ? 2 : 0;           // row 0 live
+struct QuantScale {
+	uint32_t q, q64;    // q and q << 6
+	uint32_t m_hi;      // floor(2^32 / 2q) + 1: level of t = y + q
+	uint32_t m_lo;      // floor(2^32 / 128q) + 1: level of t = 64 (y + q) + junk < 64
+	uint32_t q22;       // q << 22: a word's upper entry is a coefficient iff word >= q22
+	__device__ __forceinline__ explicit QuantScale(int qs)
+		: q((uint32_t)qs), q64((uint32_t)qs << 6), m_hi(c_qmagic[qs].x), m_lo(c_qmagic[qs].y), q22((uint32_t)qs << 22) {}
+};
+
+template <bool UPPER>
+__device__ __forceinline__ uint32_t entry_level(uint32_t word, const QuantScale &k) {
+	return UPPER ? __umulhi((word >> 22) + k.q, k.m_hi) : __umulhi((word & 0xFFFFu) + k.q64, k.m_lo);
 }
 
-// Loads N (<= 4) magnitude rows starting at row R0 of block (group, lane).
-template <int R0, int N>
-__device__ __forceinline__ void load_rows(const uint4 *__restrict__ gp, uint32_t (&w)[4 * N]) {
-#pragma unroll
-	for (int j = 0; j < N; j++) {
-		uint4 r = gp[(R0 + j) * 32];
-		w[4 * j + 0] = r.x; w[4 * j + 1] = r.y; w[4 * j + 2] = r.z; w[4 * j + 3] = r.w;
+template <bool UPPER>
+__device__ __forceinline__ uint32_t entry_pos(uint32_t word) {
+	return UPPER ? (word >> 16) & 63u : word & 63u;
+}
+
+// lenlut1 = the length table minus one byte: run = pos - prev - 1, and a padding entry (level 0,
+// position 0, met only while prev is still 0) reads the zero guard byte in front of the table.
+template <bool UPPER>
+__device__ __forceinline__ void price_entry(uint32_t word, const QuantScale &k, const uint8_t *lenlut1, uint32_t &bits,
+                                            uint32_t &prev) {
+	const uint32_t lv = entry_level<UPPER>(word, k);
+	const uint32_t pos = entry_pos<UPPER>(word);
+	bits += lenlut1[imad(min(lv, 63u), 64u, pos) - prev];
+	prev = lv ? pos : prev;
+}
+
+// AC bit cost of the block whose list occupies rows 0..nrows-1 of (group, lane).
+__device__ __forceinline__ int ac_bits(const uint4 *__restrict__ gp, int nrows, const QuantScale &k, const uint8_t *lenlut1) {
+	uint32_t bits = 0, prev = 0;
+	uint4 next = gp[(nrows > 0 ? nrows - 1 : 0) * 32];   // the row after this one is in flight while this one is priced
+	for (int r = nrows - 1; r >= 0; r--) {
+		const uint4 w = next;
+		next = gp[(r > 0 ? r - 1 : 0) * 32];
+		price_entry<true>(w.w, k, lenlut1, bits, prev);
+		price_entry<false>(w.w, k, lenlut1, bits, prev);
+		price_entry<true>(w.z, k, lenlut1, bits, prev);
+		price_entry<false>(w.z, k, lenlut1, bits, prev);
+		price_entry<true>(w.y, k, lenlut1, bits, prev);
+		price_entry<false>(w.y, k, lenlut1, bits, prev);
+		price_entry<true>(w.x, k, lenlut1, bits, prev);
+		price_entry<false>(w.x, k, lenlut1, bits, prev);
 	}
-}
-
-// |coef| number i of the loaded rows
-template <int N>
-__device__ __forceinline__ uint32_t mag_at(const uint32_t (&w)[4 * N], int i) {
-	return (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
-}
-
-// Prices the AC coefficients of rows R0..R0+N-1 (the pricing half of encode_dct_block).
-// qpar: the current q's (reciprocal, half step) pairs in shared memory.
-template <int R0, int N>
-__device__ __forceinline__ void price_rows(const uint4 *__restrict__ gp, const uint2 *qpar, const uint8_t *lenlut,
-                                           uint32_t &bits, uint32_t &run) {
-	uint32_t w[4 * N];
-	load_rows<R0, N>(gp, w);
-	const uint2 *qp = qpar + 8 * R0;
-#pragma unroll
-	for (int i = (R0 ? 0 : 1); i < 8 * N; i++) {
-		uint2 p = qp[i];
-		uint32_t lv = __umulhi(mag_at<N>(w, i) + p.y, p.x);
-		uint32_t m = min(lv, 63u);
-		bits = imad(lenlut[imad(m, 64u, run)], 1u, bits);
-		uint32_t z = imad(lv, 1u, 0xFFFFFFFFu) >> 31;      // 1 when the level is zero (lv < 2^31)
-		run = imad(run, z, z);                              // (run + 1) * z
-	}
-}
-
-// AC bit cost of one block whose rows >= NROWS are known to quantise to zero.
-template <int NROWS>
-__device__ __forceinline__ int ac_bits_prefix(const uint4 *__restrict__ gp, const uint2 *qpar, const uint8_t *lenlut) {
-	uint32_t bits = 0, run = 0;
-	if (NROWS > 0) price_rows<0, (NROWS < 4 ? NROWS : 4)>(gp, qpar, lenlut, bits, run);
-	if (NROWS > 4) price_rows<4, (NROWS > 4 ? NROWS - 4 : 1)>(gp, qpar, lenlut, bits, run);
 	return (int)bits;
 }
 
-__device__ __forceinline__ int ac_bits(const uint4 *__restrict__ gp, const uint2 *qpar, const uint2 *cpar, const uint8_t *lenlut, int prefix) {
-	if (prefix == 8) return ac_bits_prefix<8>(gp, cpar, lenlut);   // full blocks: reciprocals via the constant bank
-	if (prefix == 4) return ac_bits_prefix<4>(gp, qpar, lenlut);
-	if (prefix == 2) return ac_bits_prefix<2>(gp, qpar, lenlut);
-	return 0;
-}
-
-// Emit, convergent part: quantise rows R0..R0+N-1, park min(level,63) in the thread's column of
-// the level staging area and return their nonzero mask (bit i = coefficient 8*R0 + i).
-template <int R0, int N>
-__device__ __forceinline__ uint32_t stage_rows(const uint4 *__restrict__ gp, const uint2 *qpar, uint8_t *lev, int lev_stride) {
-	uint32_t w[4 * N];
-	load_rows<R0, N>(gp, w);
-	const uint2 *qp = qpar + 8 * R0;
-	uint32_t nz = 0;
-#pragma unroll
-	for (int i = (R0 ? 0 : 1); i < 8 * N; i++) {
-		uint2 p = qp[i];
-		uint32_t m = min(__umulhi(mag_at<N>(w, i) + p.y, p.x), 63u);
-		lev[(8 * R0 + i) * lev_stride] = (uint8_t)m;
-		nz = imad(min(m, 1u), 1u << i, nz);
+// Emit, convergent part: parks up to four list rows (rows r0..r0+n-1) in the thread's column
+// of the staging area (word j of the thread at stage[j * stride]) and returns the mask of
+// entries that are coefficients at this quant scale: bit 31 - e for local entry e = 8 * row + k,
+// so that walking the set bits upwards visits the coefficients in ascending zig-zag order.
+__device__ __forceinline__ uint32_t stage_rows(const uint4 *__restrict__ gp, int r0, int n, const QuantScale &k,
+                                               uint32_t *stage, int stride) {
+	uint32_t live = 0;
+	for (int j = n - 1; j >= 0; j--) {
+		const uint4 w = gp[(r0 + j) * 32];
+		stage[(4 * j + 0) * stride] = w.x;
+		stage[(4 * j + 1) * stride] = w.y;
+		stage[(4 * j + 2) * stride] = w.z;
+		stage[(4 * j + 3) * stride] = w.w;
+		uint32_t row = 0;   // bit 7 - e for entry e of this row
+		row |= (w.w >= k.q22) ? 0x01u : 0u;
+		row |= ((w.w & 0xFFFFu) >= k.q64) ? 0x02u : 0u;
+		row |= (w.z >= k.q22) ? 0x04u : 0u;
+		row |= ((w.z & 0xFFFFu) >= k.q64) ? 0x08u : 0u;
+		row |= (w.y >= k.q22) ? 0x10u : 0u;
+		row |= ((w.y & 0xFFFFu) >= k.q64) ? 0x20u : 0u;
+		row |= (w.x >= k.q22) ? 0x40u : 0u;
+		row |= ((w.x & 0xFFFFu) >= k.q64) ? 0x80u : 0u;
+		live |= row << (24 - 8 * j);
 	}
-	return nz;
-}
-
-template <int NROWS>
-__device__ __forceinline__ void stage_prefix(const uint4 *__restrict__ gp, const uint2 *qpar, uint8_t *lev, int lev_stride,
-                                             uint32_t &nz_lo, uint32_t &nz_hi) {
-	nz_lo = NROWS > 0 ? stage_rows<0, (NROWS < 4 ? (NROWS > 0 ? NROWS : 1) : 4)>(gp, qpar, lev, lev_stride) : 0u;
-	nz_hi = NROWS > 4 ? stage_rows<4, (NROWS > 4 ? NROWS - 4 : 1)>(gp, qpar, lev, lev_stride) : 0u;
-}
-
-__device__ __forceinline__ void stage_levels(const uint4 *__restrict__ gp, const uint2 *qpar, const uint2 *cpar, uint8_t *lev, int lev_stride,
-                                             int prefix, uint32_t &nz_lo, uint32_t &nz_hi) {
-	nz_lo = nz_hi = 0;
-	if (prefix == 8) stage_prefix<8>(gp, cpar, lev, lev_stride, nz_lo, nz_hi);
-	else if (prefix == 4) stage_prefix<4>(gp, qpar, lev, lev_stride, nz_lo, nz_hi);
-	else if (prefix == 2) stage_prefix<2>(gp, qpar, lev, lev_stride, nz_lo, nz_hi);
+	return live;
 }
 
 // Appends MSB-first codes at an arbitrary bit position of the 32-bit-word stream image. Words
@@ -460,19 +448,17 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	{
 		uint8_t *p = smem_raw;
 		auto take = [&](size_t bytes) { uint8_t *at = p; p += (bytes + 15) & ~(size_t)15; return at; };
-		s.lenlut = take(64 * 64);
+		s.lenlut = take(16 + 64 * 64) + 16;
 		s.vlc = reinterpret_cast<uint32_t *>(take(4 * 64 * 64));
 		s.misc = reinterpret_cast<uint32_t *>(take(4 * (8 + 4 * 32)));
-		s.qpar = reinterpret_cast<uint2 *>(take(8 * 2 * 64));
 		s.stream = reinterpret_cast<uint32_t *>(SMEM_STREAM ? take(4 * (size_t)stream_words) : p);
 		s.dctab = reinterpret_cast<uint32_t *>(V3 ? take(4 * 1024) : p);
 		s.gtot = reinterpret_cast<uint32_t *>(take(4 * (size_t)(nsgroups + 1)));
-		s.rowq = reinterpret_cast<uint2 *>(take(8 * (size_t)ngroups));
+		s.grows = take((size_t)ngroups);
 		s.lens = reinterpret_cast<uint16_t *>(take(2 * (size_t)padded));
 		s.dcval = reinterpret_cast<int16_t *>(V3 ? take(2 * (size_t)padded) : p);
-		s.lev = p;
+		s.stage = reinterpret_cast<uint32_t *>(p);
 	}
-	const int lev_stride = bs_lev_stride(T);
 	uint32_t *stream = SMEM_STREAM ? s.stream : gstream + (size_t)f * gstream_stride;
 
 	const uint4 *fc = coefs + (size_t)f * frame_stride_u4;
@@ -486,24 +472,24 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 
 	for (int i = tid; i < 64 * 64 / 4; i += T)
 		reinterpret_cast<uint32_t *>(s.lenlut)[i] = reinterpret_cast<const uint32_t *>(c_lenlut)[i];
+	if (tid < 4) reinterpret_cast<uint32_t *>(s.lenlut - 16)[tid] = 0;
 	for (int i = tid; i < 64 * 64; i += T) s.vlc[i] = g_vlc[i];
 	if (V3) for (int i = tid; i < 1024; i += T) s.dctab[i] = c_dcvlc[i];
 	for (int i = tid; i < words; i += T) stream[i] = 0;
 	if (tid < 8) s.misc[tid] = 0;
 	for (int b = nblk + tid; b < padded; b += T) s.lens[b] = 0;   // scan padding
-	for (int i = tid; i < 64; i += T) s.qpar[64 + i] = c_qparam[64 + i];   // q = 1
 	for (int g = tid; g < ngroups; g += T) {
-		uint4 r8 = fc[(size_t)g * (BS_U4_PER_BLOCK * 32) + 8 * 32];   // lane 0's sign row carries the group's rowq
-		s.rowq[g] = make_uint2(r8.z, r8.w);
+		// every lane's meta row carries the group's longest list
+		uint32_t longest = reinterpret_cast<const uint32_t *>(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + BS_META_ROW * 32)[3];
+		s.grows[g] = (uint8_t)((min(longest, 63u) + 7) >> 3);
 	}
 	if (V3) {
 		for (int pi = tid; pi < ngroups * 32; pi += T) {
 			int b = bs_plane_to_block(pi, cpad, nmb);
 			if (b < 0) continue;
 			const uint4 *gp = fc + (size_t)(pi >> 5) * (BS_U4_PER_BLOCK * 32) + (pi & 31);
-			uint32_t w0 = reinterpret_cast<const uint32_t *>(gp)[0];
-			uint32_t sg = reinterpret_cast<const uint32_t *>(gp + 8 * 32)[0];
-			s.dcval[b] = (int16_t)quant_dc(w0 & 0xFFFFu, sg & 1u);
+			const uint4 meta = gp[BS_META_ROW * 32];
+			s.dcval[b] = (int16_t)quant_dc(meta.z & 0xFFFFu, meta.x & 1u);
 		}
 	}
 	__syncthreads();
@@ -519,19 +505,15 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	int q = 1;
 	uint32_t total_bits = 0;
 	for (; q < 64; q++) {
-		// next pass's reciprocals; readers only touch them after this pass's closing barrier
-		if (q < 63)
-			for (int i = tid; i < 64; i += T) s.qpar[((q + 1) & 1) * 64 + i] = c_qparam[(q + 1) * 64 + i];
-		const uint2 *qpar = s.qpar + (q & 1) * 64;
+		const QuantScale qs(q);
 		// the (usually busier) luma groups at the high end of the plane go first; drawing groups
 		// from a shared ticket counter instead of this static round-robin measured no better
 		uint32_t *total = &s.misc[q % 3];
 		for (int g = ngroups - 1 - wid; g >= 0; g -= nw) {
 			const int b = bs_plane_to_block(g * 32 + lane, cpad, nmb);
-			const int prefix = live_prefix(s.rowq[g], q);
 			int bits = 0;
 			if (b >= 0) {
-				bits = ac_bits(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane, qpar, c_qparam + q * 64, s.lenlut, prefix);
+				bits = ac_bits(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane, s.grows[g], qs, s.lenlut - 1);
 				bits += 2 + (V3 ? (int)(dc_code(b) >> 24) : 10);
 				s.lens[b] = (uint16_t)bits;
 			}
@@ -613,54 +595,46 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	__syncthreads();
 
 	// ---- (3) emit --------------------------------------------------------------------------
-	// Per block: a convergent pass re-quantises all 63 AC coefficients, parks min(level,63) in
-	// the thread's shared-memory column and builds a 64-bit nonzero mask; the codes are then
-	// produced by walking the set bits only (runs fall out of the bit positions).
+	// Per block, for each half of its list (rows 4.. first: they hold the lower positions): a
+	// convergent pass parks the rows in the thread's shared-memory column and marks the entries
+	// that are coefficients at q; the codes are then produced by walking the marks only.
 	{
-		const uint2 *qpar = s.qpar + (q & 1) * 64;
-		uint8_t *lev = s.lev + tid;
+		const QuantScale qs(q);
+		uint32_t *stage = s.stage + tid;
 		uint32_t nnz = 0;
 		for (int g = ngroups - 1 - wid; g >= 0; g -= nw) {
 			const int b = bs_plane_to_block(g * 32 + lane, cpad, nmb);
 			if (b < 0) continue;
 			const uint4 *gp = fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane;
-			uint32_t nz_lo, nz_hi;
-			const uint32_t dc_mag = reinterpret_cast<const uint32_t *>(gp)[0] & 0xFFFFu;
-			stage_levels(gp, qpar, c_qparam + q * 64, lev, lev_stride, live_prefix(s.rowq[g], q), nz_lo, nz_hi);
-			uint4 sg = gp[8 * 32];
+			const uint4 meta = gp[BS_META_ROW * 32];
+			const int nrows = s.grows[g];
 			BitWriter bw;
 			bw.begin(stream, s.gtot[b >> 5] + s.lens[b]);
 			if (V3) {
 				uint32_t e = dc_code(b);
 				bw.put((int)(e >> 24), e & 0xFFFFFFu);
 			} else {
-				bw.put(10, (uint32_t)quant_dc(dc_mag, sg.x & 1u) & 0x3FFu);
+				bw.put(10, (uint32_t)quant_dc(meta.z & 0xFFFFu, meta.x & 1u) & 0x3FFu);
 			}
-			nnz += __popc(nz_lo) + __popc(nz_hi);
 			int prev = 0;
-#pragma unroll
-			for (int half = 0; half < 2; half++) {
-				uint32_t nz = half ? nz_hi : nz_lo;
-				const uint32_t signs = half ? sg.y : sg.x;
-				const uint8_t *lv = lev + 32 * half * lev_stride;
-				while (nz) {
-					int i = __ffs((int)nz) - 1;
-					nz &= nz - 1;
-					int pos = 32 * half + i;
-					int run = pos - prev - 1;
+			for (int r0 = nrows > 4 ? 4 : 0; r0 >= 0; r0 -= 4) {
+				uint32_t live = stage_rows(gp, r0, min(nrows - r0, 4), qs, stage, T);
+				nnz += __popc(live);
+				while (live) {
+					const int e = 32 - __ffs((int)live);   // local entry, highest (= lowest position) first
+					live &= live - 1;
+					const uint32_t word = stage[(e >> 1) * T];
+					const uint32_t ent = (e & 1) ? word >> 16 : word & 0xFFFFu;
+					const int pos = (int)(ent & 63u);
+					const uint32_t lvl = __umulhi((ent >> 6) + qs.q, qs.m_hi);
+					const int run = pos - prev - 1;
 					prev = pos;
-					uint32_t m = lv[i * lev_stride];
-					uint32_t neg = (signs >> i) & 1u;
-					uint32_t e = s.vlc[(m << 6) | run];
-					if (e & 0xFFFFFFu) {
-						bw.put((int)(e >> 24), (e & 0xFFFFFFu) | neg);
+					const uint32_t neg = (pos & 32 ? meta.y >> (pos & 31) : meta.x >> pos) & 1u;
+					const uint32_t code = s.vlc[(min(lvl, 63u) << 6) | run];
+					if (code & 0xFFFFFFu) {
+						bw.put((int)(code >> 24), (code & 0xFFFFFFu) | neg);
 					} else {
-						// escape: exact level from the coefficient plane, clamped to [-512, 510]
-						// (mdec.c:262-265), as 10-bit two's complement
-						uint32_t word = reinterpret_cast<const uint32_t *>(gp + (pos >> 3) * 32)[(pos >> 1) & 3];
-						uint32_t mag = (pos & 1) ? (word >> 16) : (word & 0xFFFFu);
-						uint2 pq = qpar[pos];
-						uint32_t lvl = __umulhi(mag + pq.y, pq.x);
+						// escape: the level clamped to [-512, 510] (mdec.c:262-265) as 10-bit two's complement
 						int level = neg ? -(int)min(lvl, 0x200u) : (int)min(lvl, 0x1FEu);
 						bw.put(BS_AC_ESCAPE_BITS, (1u << 16) | ((uint32_t)run << 10) | ((uint32_t)level & 0x3FFu));
 					}
@@ -706,17 +680,16 @@ size_t bs_pack_smem_bytes(bool v3, bool smem_stream, const BsGeometry &geo, int 
 	size_t padded = (size_t)geo.nsgroups * 32;
 	size_t n = 0;
 	auto take = [&](size_t bytes) { n += (bytes + 15) & ~(size_t)15; };
-	take(64 * 64);                        // lenlut
+	take(16 + 64 * 64);                   // guard + lenlut
 	take(4 * 64 * 64);                    // vlc
 	take(4 * (8 + 4 * 32));               // misc
-	take(8 * 2 * 64);                     // qpar
 	if (smem_stream) take(4 * (size_t)((max_size_bound + 3) / 4 + 2));
 	if (v3) take(4 * 1024);               // dctab
 	take(4 * (size_t)(geo.nsgroups + 1)); // gtot
-	take(8 * (size_t)ngroups);            // rowq
+	take((size_t)ngroups);                // grows
 	take(2 * padded);                     // lens
 	if (v3) take(2 * padded);             // dcval
-	take(64 * (size_t)bs_lev_stride(threads));   // lev
+	take(64 * (size_t)threads);           // stage: 16 words per thread
 	return n;
 }
 

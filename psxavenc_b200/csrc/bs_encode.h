@@ -14,9 +14,11 @@ constexpr int BS_DCT_THREADS = 128;
 #define BS_DCT_MIN_CTAS 7   // 72 registers, 28 warps per SM: measured +7.5 % over 6 (80 registers)
 #endif
 constexpr int BS_PACK_MAX_THREADS = 640;
-// per block in the coefficient plane: 8 uint4 of |coef| (u16 pairs, zig-zag order) + 1 uint4
-// holding the 64-bit sign mask
+// per block in the coefficient plane: up to 8 uint4 rows of list entries ((y << 6) | zig-zag
+// position, 16 bits each, highest position first, zero padded; only the rows the group's longest
+// list needs are written) + 1 meta uint4: sign mask lo/hi, |DC| | list length << 16, longest list
 constexpr int BS_U4_PER_BLOCK = 9;
+constexpr int BS_META_ROW = 8;
 // the bitstream image lives in shared memory while the CTA's total stays below this, else in
 // global memory
 constexpr size_t BS_SMEM_BUDGET = 200 * 1024;
@@ -72,13 +74,6 @@ struct BsStrLayout {
 
 void bs_upload_tables();
 size_t bs_pack_smem_bytes(bool v3, bool smem_stream, const BsGeometry &geo, int max_size_bound, int threads);
-
-// Row stride (bytes) of the per-thread level staging columns: threads rounded so that the
-// stride in 32-bit words is odd, which spreads a warp's scattered byte reads over the banks.
-__host__ __device__ inline int bs_lev_stride(int threads) {
-	int s = (threads + 3) & ~3;
-	return ((s >> 2) & 1) ? s : s + 4;
-}
 
 cudaError_t bs_launch_dct(int fdct_variant, const uint8_t *d_frames, size_t frame_bytes, int n, int width, int height,
                           const BsGeometry &geo, uint4 *d_coefs, cudaStream_t stream);

@@ -71,7 +71,8 @@ size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // ======================================================================================
 
 struct psxb200_bs_encoder {
-	int codec, width, height, fdct, max_batch, host_chunk, pack_threads, pack_min_ctas = 3;
+	int codec, width, height, fdct, max_batch, host_chunk, pack_threads, pack_min_ctas = 3, sm_count = 0;
+	bool pack_threads_forced = false;   // PSXB200_PACK_THREADS given: no small-batch override
 	size_t frame_bytes;
 	BsGeometry geo;
 	// coefficient planes: [0] serves the device API and host slot 0, [1] host slot 1
@@ -138,6 +139,13 @@ extern "C" psxb200_bs_encoder_t *psxb200_bs_create(int codec, int width, int hei
 	}
 	auto *enc = new psxb200_bs_encoder(codec, width, height, fdct_variant, max_batch);
 	enc->pack_threads = bs_pick_threads(enc->geo);
+	enc->pack_threads_forced = getenv("PSXB200_PACK_THREADS") != nullptr;
+	{
+		int dev = 0;
+		if (cudaGetDevice(&dev) != cudaSuccess ||
+		    cudaDeviceGetAttribute(&enc->sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+			enc->sm_count = 0;
+	}
 	if (const char *env = getenv("PSXB200_PACK_MIN_CTAS")) enc->pack_min_ctas = atoi(env);
 	if (const char *env = getenv("PSXB200_HOST_CHUNK")) enc->host_chunk = std::max(1, std::min(max_batch, atoi(env)));
 	bs_upload_tables();
@@ -174,7 +182,14 @@ static int bs_encode_chunked(psxb200_bs_encoder *enc, uint4 *d_coefs, int n, con
                              psxb200_bs_result_t *d_results, cudaStream_t stream, const BsStrLayout *str_batch = nullptr) {
 	uint32_t *gstream = nullptr;
 	size_t gstride = 0;
-	if (bs_pack_smem_bytes(enc->codec != 0, true, enc->geo, max_size_bound, enc->pack_threads) > BS_SMEM_BUDGET) {
+	// Few frames (the drop-in calls encode one at a time): every CTA has an SM to itself, so the
+	// frame's latency is what counts and the widest CTA wins (88 vs 102 us per drop-in frame).
+	int threads = enc->pack_threads, min_ctas = enc->pack_min_ctas;
+	if (n <= enc->sm_count && !enc->pack_threads_forced) {
+		threads = 32 * std::max(1, std::min(BS_PACK_MAX_THREADS / 32, enc->geo.ngroups));
+		min_ctas = 1;
+	}
+	if (bs_pack_smem_bytes(enc->codec != 0, true, enc->geo, max_size_bound, threads) > BS_SMEM_BUDGET) {
 		gstride = (size_t)(max_size_bound + 3) / 4 + 2;
 		CU_TRY(enc->gstream.reserve(gstride * enc->max_batch));
 		gstream = enc->gstream.ptr;
@@ -190,7 +205,7 @@ static int bs_encode_chunked(psxb200_bs_encoder *enc, uint4 *d_coefs, int n, con
 			str = *str_batch;
 			str.frame_index0 += first;   // sector0 stays the batch's: the kernel positions frames absolutely
 		}
-		CU_TRY(bs_launch_pack(enc->codec, enc->pack_threads, enc->pack_min_ctas, m, d_coefs, enc->geo,
+		CU_TRY(bs_launch_pack(enc->codec, threads, min_ctas, m, d_coefs, enc->geo,
 		                      str_batch ? nullptr : d_max_sizes + first, max_size_bound,
 		                      str_batch ? d_out : d_out + (size_t)first * out_stride, out_stride, d_results + first, gstream,
 		                      gstride, str, stream));
