@@ -125,21 +125,19 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
 	const bool chroma = b < cpad;   // warp-uniform: cpad is a multiple of 32
 	const bool active = chroma ? b < 2 * nmb : b - cpad < 4 * nmb;
 
-	uint32_t sign_lo = 0, sign_hi = 0, dc_mag = 0;
-	uint16_t *const col = s_list + threadIdx.x;
-	// the append cursor as a 32-bit shared-space address: one add per bump, no generic pointers
-	const uint32_t col_addr = (uint32_t)__cvta_generic_to_shared(col);
-	uint32_t tail = col_addr;
 	uint4 *dst = coefs + (size_t)f * frame_stride_u4 + (size_t)(b >> 5) * (BS_U4_PER_BLOCK * 32) + (b & 31);
 
-	if (active) {
+	int v[64];   // samples, then coefficients, then their y values (raster order)
+	if (!active) {
+#pragma unroll
+		for (int i = 0; i < 64; i++) v[i] = 0;
+	} else {
 		// macroblocks in bitstream order: columns outermost, rows next (mdec.c:689-704)
 		int mb = chroma ? b >> 1 : (b - cpad) >> 2;
 		int k = chroma ? b & 1 : 2 + ((b - cpad) & 3);
 		int mx = mbh_magic ? (int)__umulhi((uint32_t)mb, mbh_magic) : mb, my = mb - mx * mbh;   // mb / mbh (magic 0: mbh == 1)
 		const uint8_t *fr = frames + (size_t)f * frame_bytes;
 
-		int v[64];
 		if (chroma) {
 			// interleaved CrCb plane: Cr at even bytes, Cb at odd (mdec.c:627-628)
 			const uint8_t *p = fr + (size_t)width * height + (size_t)width * (my * 8) + mx * 16;
@@ -173,43 +171,69 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
 		// applied once here.
 		fdct8x8<VARIANT>(v);
 		v[0] -= 8192;
+	}
 
-		// Coefficients are visited in descending zig-zag order: each sign is shifted into its
-		// mask with one funnel shift (coefficient i ends up at bit i of its half), and the list
-		// comes out with the highest position first — the pack kernel walks it backwards.
+	// Coefficients are visited in descending zig-zag order: each sign is shifted into its mask
+	// with one funnel shift (coefficient i ends up at bit i of its half), and the list comes out
+	// with the highest position first — the pack kernel walks it backwards. The y values replace
+	// the coefficients in v[] for the dense format below.
+	uint32_t sign_lo = 0, sign_hi = 0, dc_mag = 0;
+	uint16_t *const col = s_list + threadIdx.x;
+	// the append cursor as a 32-bit shared-space address: one add per bump, no generic pointers
+	const uint32_t col_addr = (uint32_t)__cvta_generic_to_shared(col);
+	uint32_t tail = col_addr;
 #pragma unroll
-		for (int i = 63; i >= 0; i--) {
-			const int c = v[zigzag_at(i)];
-			if (i < 32) sign_lo = __funnelshift_l((uint32_t)c, sign_lo, 1);
-			else sign_hi = __funnelshift_l((uint32_t)c, sign_hi, 1);
-			const uint32_t mag = (uint32_t)abs(c);
-			if (i == 0) {
-				dc_mag = mag;   // the DC term has its own fixed step (mdec.c:447, 671)
-			} else {
-				const uint32_t y = __umulhi(mag, ymagic_at(i));   // floor(2|c| / quant[i])
-				if (y) {
-					asm volatile("st.shared.u16 [%0], %1;" ::"r"(tail), "h"((uint16_t)((y << 6) | (uint32_t)i)) : "memory");
-					tail += 2 * BS_DCT_THREADS;
-				}
+	for (int i = 63; i >= 0; i--) {
+		const int c = v[zigzag_at(i)];
+		if (i < 32) sign_lo = __funnelshift_l((uint32_t)c, sign_lo, 1);
+		else sign_hi = __funnelshift_l((uint32_t)c, sign_hi, 1);
+		const uint32_t mag = (uint32_t)abs(c);
+		if (i == 0) {
+			dc_mag = mag;   // the DC term has its own fixed step (mdec.c:447, 671)
+			v[0] = 0;
+		} else {
+			const uint32_t y = __umulhi(mag, ymagic_at(i));   // floor(2|c| / quant[i])
+			v[zigzag_at(i)] = (int)y;
+			if (y) {
+				asm volatile("st.shared.u16 [%0], %1;" ::"r"(tail), "h"((uint16_t)((y << 6) | (uint32_t)i)) : "memory");
+				tail += 2 * BS_DCT_THREADS;
 			}
 		}
 	}
 
-	// The group's lists are stored as rows of 8 entries per lane, as many rows as its longest
-	// list needs; shorter lists are zero padded (y = 0: never a coefficient).
 	const int count = (int)(tail - col_addr) / (2 * BS_DCT_THREADS);
 	const int longest = (int)__reduce_max_sync(0xFFFFFFFFu, (uint32_t)count);
-	const int nrows = (longest + 7) >> 3;
-	for (int r = 0; r < nrows; r++) {
-		const uint16_t *e = col + 8 * r * BS_DCT_THREADS;
-		uint32_t w[4];
+	// Lists pay off while the group's longest one stays well below the 63 possible entries. A
+	// group whose longest list would fill (nearly) all eight rows anyway is stored dense instead:
+	// y of all 64 positions in zig-zag order (position implicit, DC slot 0), which the pack
+	// kernel handles with straight-line code that needs no positions (cheaper per coefficient).
+	const bool dense = longest >= BS_DENSE_MIN;
+	if (dense) {
 #pragma unroll
-		for (int t = 0; t < 4; t++)
-			w[t] = (uint32_t)e[(2 * t) * BS_DCT_THREADS] | ((uint32_t)e[(2 * t + 1) * BS_DCT_THREADS] << 16);
-		dst[r * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+		for (int j = 0; j < 8; j++) {
+			uint32_t w[4];
+#pragma unroll
+			for (int t = 0; t < 4; t++)
+				w[t] = (uint32_t)v[zigzag_at(8 * j + 2 * t)] | ((uint32_t)v[zigzag_at(8 * j + 2 * t + 1)] << 16);
+			dst[j * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+		}
+	} else {
+		// rows of 8 entries per lane, as many as the longest list needs; shorter lists are zero
+		// padded (y = 0: never a coefficient)
+		const int nrows = (longest + 7) >> 3;
+		for (int r = 0; r < nrows; r++) {
+			const uint16_t *e = col + 8 * r * BS_DCT_THREADS;
+			uint32_t w[4];
+#pragma unroll
+			for (int t = 0; t < 4; t++)
+				w[t] = (uint32_t)e[(2 * t) * BS_DCT_THREADS] | ((uint32_t)e[(2 * t + 1) * BS_DCT_THREADS] << 16);
+			dst[r * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+		}
 	}
 	// meta row: signs by zig-zag position, |DC| and this block's list length, the group's longest
-	dst[BS_META_ROW * 32] = make_uint4(sign_lo, sign_hi, dc_mag | ((uint32_t)count << 16), (uint32_t)longest);
+	// list with BS_DENSE_FLAG when the rows are dense
+	dst[BS_META_ROW * 32] = make_uint4(sign_lo, sign_hi, dc_mag | ((uint32_t)count << 16),
+	                                   (uint32_t)longest | (dense ? BS_DENSE_FLAG : 0u));
 }
 
 // ---- kernel 2: quant-scale search + bit packing ------------------------------------------
@@ -218,7 +242,7 @@ struct PackSmem {
 	uint32_t *stream;   // bitstream image, 32-bit words, first stream bit = bit 31 of word 0
 	uint32_t *dctab;    // v3: DC delta codes, [0..511] chroma, [512..1023] luma (len<<24 | code)
 	uint32_t *gtot;     // per group bit totals -> exclusive group bases
-	uint8_t *grows;     // per plane group: list rows in use (longest list of its 32 blocks, from bs_dct_kernel)
+	uint8_t *grows;     // per plane group: list rows in use (longest list of its 32 blocks), or 0x80: dense rows
 	uint32_t *misc;     // [0..2] rotating frame totals, [3] nonzero AC count, [8..] scan scratch
 	uint32_t *vlc;      // [min(level,63)][run] -> (len<<24)|code, see g_vlc
 	uint16_t *lens;     // per block bit length at the current q; after the scan: exclusive offset in its group
@@ -296,6 +320,54 @@ __device__ __forceinline__ int ac_bits(const uint4 *__restrict__ gp, int nrows, 
 		price_entry<false>(w.x, k, lenlut1, bits, prev);
 	}
 	return (int)bits;
+}
+
+// The same for a dense group (all 64 y values in zig-zag order, position implicit), one half
+// (four rows, 32 positions) at a time to bound the register footprint.
+template <int HALF>
+__device__ __forceinline__ void price_dense_half(const uint4 *__restrict__ gp, const QuantScale &k, const uint8_t *lenlut,
+                                                 uint32_t &bits, uint32_t &run) {
+	uint32_t w[16];
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		const uint4 r = gp[(4 * HALF + j) * 32];
+		w[4 * j + 0] = r.x; w[4 * j + 1] = r.y; w[4 * j + 2] = r.z; w[4 * j + 3] = r.w;
+	}
+#pragma unroll
+	for (int i = (HALF ? 0 : 1); i < 32; i++) {
+		const uint32_t y = (i & 1) ? w[i >> 1] >> 16 : w[i >> 1] & 0xFFFFu;
+		const uint32_t lv = __umulhi(y + k.q, k.m_hi);
+		bits = imad(lenlut[imad(min(lv, 63u), 64u, run)], 1u, bits);
+		const uint32_t z = imad(lv, 1u, 0xFFFFFFFFu) >> 31;   // 1 when the level is zero
+		run = imad(run, z, z);                                 // (run + 1) * z
+	}
+}
+
+__device__ __forceinline__ int ac_bits_dense(const uint4 *__restrict__ gp, const QuantScale &k, const uint8_t *lenlut) {
+	uint32_t bits = 0, run = 0;
+	price_dense_half<0>(gp, k, lenlut, bits, run);
+	price_dense_half<1>(gp, k, lenlut, bits, run);
+	return (int)bits;
+}
+
+// Emit, convergent part for a dense group: parks rows 4*half..4*half+3 in the thread's column and
+// returns the mask of positions 32*half + e that are coefficients at this quant scale (bit e).
+__device__ __forceinline__ uint32_t stage_dense(const uint4 *__restrict__ gp, int half, const QuantScale &k,
+                                                uint32_t *stage, int stride) {
+	uint32_t live = 0;
+	const uint32_t q16 = k.q << 16;
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		const uint4 r = gp[(4 * half + j) * 32];
+		const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+		for (int t = 0; t < 4; t++) {
+			stage[(4 * j + t) * stride] = w[t];
+			live |= ((w[t] & 0xFFFFu) >= k.q ? 1u : 0u) << (8 * j + 2 * t);
+			live |= (w[t] >= q16 ? 1u : 0u) << (8 * j + 2 * t + 1);
+		}
+	}
+	return live;
 }
 
 // Emit, convergent part: parks up to four list rows (rows r0..r0+n-1) in the thread's column
@@ -479,9 +551,9 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	if (tid < 8) s.misc[tid] = 0;
 	for (int b = nblk + tid; b < padded; b += T) s.lens[b] = 0;   // scan padding
 	for (int g = tid; g < ngroups; g += T) {
-		// every lane's meta row carries the group's longest list
+		// every lane's meta row carries the group's longest list and the dense flag
 		uint32_t longest = reinterpret_cast<const uint32_t *>(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + BS_META_ROW * 32)[3];
-		s.grows[g] = (uint8_t)((min(longest, 63u) + 7) >> 3);
+		s.grows[g] = (longest & BS_DENSE_FLAG) ? (uint8_t)0x80 : (uint8_t)((min(longest, 63u) + 7) >> 3);
 	}
 	if (V3) {
 		for (int pi = tid; pi < ngroups * 32; pi += T) {
@@ -513,7 +585,9 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 			const int b = bs_plane_to_block(g * 32 + lane, cpad, nmb);
 			int bits = 0;
 			if (b >= 0) {
-				bits = ac_bits(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane, s.grows[g], qs, s.lenlut - 1);
+				const uint4 *gp = fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane;
+				const int rows = s.grows[g];
+				bits = (rows & 0x80) ? ac_bits_dense(gp, qs, s.lenlut) : ac_bits(gp, rows, qs, s.lenlut - 1);
 				bits += 2 + (V3 ? (int)(dc_code(b) >> 24) : 10);
 				s.lens[b] = (uint16_t)bits;
 			}
@@ -617,26 +691,42 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 				bw.put(10, (uint32_t)quant_dc(meta.z & 0xFFFFu, meta.x & 1u) & 0x3FFu);
 			}
 			int prev = 0;
-			for (int r0 = nrows > 4 ? 4 : 0; r0 >= 0; r0 -= 4) {
-				uint32_t live = stage_rows(gp, r0, min(nrows - r0, 4), qs, stage, T);
-				nnz += __popc(live);
-				while (live) {
-					const int e = 32 - __ffs((int)live);   // local entry, highest (= lowest position) first
-					live &= live - 1;
-					const uint32_t word = stage[(e >> 1) * T];
-					const uint32_t ent = (e & 1) ? word >> 16 : word & 0xFFFFu;
-					const int pos = (int)(ent & 63u);
-					const uint32_t lvl = __umulhi((ent >> 6) + qs.q, qs.m_hi);
-					const int run = pos - prev - 1;
-					prev = pos;
-					const uint32_t neg = (pos & 32 ? meta.y >> (pos & 31) : meta.x >> pos) & 1u;
-					const uint32_t code = s.vlc[(min(lvl, 63u) << 6) | run];
-					if (code & 0xFFFFFFu) {
-						bw.put((int)(code >> 24), (code & 0xFFFFFFu) | neg);
-					} else {
-						// escape: the level clamped to [-512, 510] (mdec.c:262-265) as 10-bit two's complement
-						int level = neg ? -(int)min(lvl, 0x200u) : (int)min(lvl, 0x1FEu);
-						bw.put(BS_AC_ESCAPE_BITS, (1u << 16) | ((uint32_t)run << 10) | ((uint32_t)level & 0x3FFu));
+			// one coefficient: y at zig-zag position pos (mdec.c:484-499)
+			auto put_coef = [&](uint32_t y, int pos) {
+				const uint32_t lvl = __umulhi(y + qs.q, qs.m_hi);
+				const int run = pos - prev - 1;
+				prev = pos;
+				const uint32_t neg = (pos & 32 ? meta.y >> (pos & 31) : meta.x >> pos) & 1u;
+				const uint32_t code = s.vlc[(min(lvl, 63u) << 6) | run];
+				if (code & 0xFFFFFFu) {
+					bw.put((int)(code >> 24), (code & 0xFFFFFFu) | neg);
+				} else {
+					// escape: the level clamped to [-512, 510] (mdec.c:262-265) as 10-bit two's complement
+					int level = neg ? -(int)min(lvl, 0x200u) : (int)min(lvl, 0x1FEu);
+					bw.put(BS_AC_ESCAPE_BITS, (1u << 16) | ((uint32_t)run << 10) | ((uint32_t)level & 0x3FFu));
+				}
+			};
+			if (nrows & 0x80) {
+				for (int half = 0; half < 2; half++) {
+					uint32_t live = stage_dense(gp, half, qs, stage, T);
+					nnz += __popc(live);
+					while (live) {
+						const int e = __ffs((int)live) - 1;
+						live &= live - 1;
+						const uint32_t word = stage[(e >> 1) * T];
+						put_coef((e & 1) ? word >> 16 : word & 0xFFFFu, 32 * half + e);
+					}
+				}
+			} else {
+				for (int r0 = nrows > 4 ? 4 : 0; r0 >= 0; r0 -= 4) {
+					uint32_t live = stage_rows(gp, r0, min(nrows - r0, 4), qs, stage, T);
+					nnz += __popc(live);
+					while (live) {
+						const int e = 32 - __ffs((int)live);   // local entry, highest (= lowest position) first
+						live &= live - 1;
+						const uint32_t word = stage[(e >> 1) * T];
+						const uint32_t ent = (e & 1) ? word >> 16 : word & 0xFFFFu;
+						put_coef(ent >> 6, (int)(ent & 63u));
 					}
 				}
 			}

@@ -19,6 +19,12 @@ constexpr int BS_PACK_MAX_THREADS = 640;
 // list needs are written) + 1 meta uint4: sign mask lo/hi, |DC| | list length << 16, longest list
 constexpr int BS_U4_PER_BLOCK = 9;
 constexpr int BS_META_ROW = 8;
+// groups whose longest list reaches this many entries are stored dense (all 64 y values,
+// position implicit) instead of as lists; flagged in meta.w
+#ifndef BS_DENSE_MIN
+#define BS_DENSE_MIN 49
+#endif
+constexpr unsigned BS_DENSE_FLAG = 0x100;
 // the bitstream image lives in shared memory while the CTA's total stays below this, else in
 // global memory
 constexpr size_t BS_SMEM_BUDGET = 200 * 1024;
