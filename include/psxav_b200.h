@@ -192,7 +192,8 @@ void psxb200_bs_destroy(psxb200_bs_encoder_t *enc);
 
 /* Device-resident batch: d_frames = n NV21 frames back to back (1.5*W*H bytes each, base
  * 16-byte aligned), d_max_sizes[n] = per-frame byte budgets (frame_max_size), each
- * <= max_size_bound; d_out = n bitstream buffers out_stride bytes apart (out_stride and
+ * <= max_size_bound, or NULL when every frame's budget is max_size_bound; only bytes
+ * [0, frame_max_size) of a frame's buffer are defined; d_out = n bitstream buffers out_stride bytes apart (out_stride and
  * base multiples of 4, out_stride >= max_size_bound); d_results[n]. Asynchronous on
  * `stream` (a cudaStream_t, NULL = default stream). Returns 0, or -1 (see
  * psxb200_last_error). Frames for which no quant scale fits get quant_scale 64,

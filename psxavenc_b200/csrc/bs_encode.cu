@@ -537,7 +537,8 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	// STR mode: budget and sector position follow from the frame index alone
 	const long long str_k = (long long)str.frame_index0 + f;
 	const long long str_before = str.sector_size ? (str_k - 1) * str.sectors_num / str.sectors_den : 0;
-	int max_size = str.sector_size ? (int)(str_k * str.sectors_num / str.sectors_den - str_before) * 2016 : max_sizes[f];
+	int max_size = str.sector_size ? (int)(str_k * str.sectors_num / str.sectors_den - str_before) * 2016
+	               : max_sizes ? max_sizes[f] : max_size_bound;   // no per-frame budgets: all frames get the bound
 	if (max_size > max_size_bound) max_size = 0;   // contract violation -> frame fails
 	if (str.sector_size) out += (size_t)(str_before - str.sector0) * str.sector_size - (size_t)f * out_stride;
 	const int words = max_size > 0 ? (max_size + 3) / 4 + 2 : 0;

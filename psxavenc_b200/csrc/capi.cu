@@ -206,7 +206,7 @@ static int bs_encode_chunked(psxb200_bs_encoder *enc, uint4 *d_coefs, int n, con
 			str.frame_index0 += first;   // sector0 stays the batch's: the kernel positions frames absolutely
 		}
 		CU_TRY(bs_launch_pack(enc->codec, threads, min_ctas, m, d_coefs, enc->geo,
-		                      str_batch ? nullptr : d_max_sizes + first, max_size_bound,
+		                      (str_batch || !d_max_sizes) ? nullptr : d_max_sizes + first, max_size_bound,
 		                      str_batch ? d_out : d_out + (size_t)first * out_stride, out_stride, d_results + first, gstream,
 		                      gstride, str, stream));
 		if (enc->timing) CU_TRY(enc->mark(stream));
@@ -269,7 +269,12 @@ extern "C" int psxb200_bs_encode_host(psxb200_bs_encoder_t *enc, int n, const ui
 		int m = std::min(hc, n - first);
 		cudaStream_t st = enc->streams[slot];
 		int bound = 8;
-		for (int i = 0; i < m; i++) bound = std::max(bound, h_max_sizes[first + i]);
+		bool uniform = true;   // one budget for the whole chunk: no per-frame array to upload
+		for (int i = 0; i < m; i++) {
+			bound = std::max(bound, h_max_sizes[first + i]);
+			uniform = uniform && h_max_sizes[first + i] == h_max_sizes[first];
+		}
+		uniform = uniform && h_max_sizes[first] >= 8;
 		if ((size_t)bound > out_stride && n > 1) return fail("psxb200_bs_encode_host: frame_max_size %d > out_stride", bound);
 		size_t dstride = round_up((size_t)bound, 16);
 
@@ -282,8 +287,9 @@ extern "C" int psxb200_bs_encode_host(psxb200_bs_encoder_t *enc, int n, const ui
 
 		CU_TRY(cudaMemcpyAsync(enc->in[slot].ptr, h_frames + (size_t)first * enc->frame_bytes, (size_t)m * enc->frame_bytes,
 		                       cudaMemcpyHostToDevice, st));
-		CU_TRY(cudaMemcpyAsync(enc->sizes[slot].ptr, h_max_sizes + first, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, st));
-		if (bs_encode_chunked(enc, enc->coefs[slot].ptr, m, enc->in[slot].ptr, enc->sizes[slot].ptr, bound,
+		if (!uniform)
+			CU_TRY(cudaMemcpyAsync(enc->sizes[slot].ptr, h_max_sizes + first, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, st));
+		if (bs_encode_chunked(enc, enc->coefs[slot].ptr, m, enc->in[slot].ptr, uniform ? nullptr : enc->sizes[slot].ptr, bound,
 		                      enc->out[slot].ptr, dstride, enc->res[slot].ptr, st))
 			return -1;
 		CU_TRY(cudaMemcpy2DAsync(h_out + (size_t)first * out_stride, std::max(out_stride, (size_t)bound), enc->out[slot].ptr,
