@@ -94,13 +94,15 @@ __device__ __forceinline__ void encode_unit(const int (&s)[UNIT], int qerr, int 
 	// (floor division by a power of two; nothing overflows: |x| < 2^17), which takes the left
 	// shift off the serial chain; qerr rides along in the rounding term.
 	const int down = RANGE - sh;
+	const int scale = 1 << down;   // decoding multiplies (IMAD, FMA pipe) instead of shifting: the loop is ALU-pipe bound
 	const int round_q = ((1 << (RANGE - 1)) >> sh) + qerr;
 #pragma unroll
 	for (int i = 0; i < UNIT; i++) {
 		int pred = (k1 * t1 + k2 * t2 + 32) >> 6;
 		int e = (s[i] - pred + round_q) >> down;
 		e = min(max(e, LO), HI);
-		int dec = (e << down) + pred;
+		int dec;
+		asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(dec) : "r"(e), "r"(scale), "r"(pred));   // (e << down) + pred
 		dec = min(max(dec, -0x8000), 0x7FFF);
 		int d = dec - s[i] - qerr;
 		err2 += (unsigned long long)((long long)d * d);
