@@ -45,9 +45,10 @@ namespace psxb200 {
 __constant__ uint2 c_qmagic[64];
 // [min(level,63)][run] -> code length in bits incl. sign (22 = escape), 0 for level 0.
 __constant__ uint8_t c_lenlut[64 * 64];
-// [min(level,63)][run] -> (len << 24) | code with the sign bit (LSB) clear; level 0 -> 0;
-// escape -> (22 << 24) with code 0. Copied to shared memory by every CTA.
-__device__ uint32_t g_vlc[64 * 64];
+// [min(level,41)][min(run,32)] -> (len << 24) | code with the sign bit (LSB) clear; level 0 -> 0;
+// escape (including all of row 41 and column 32) -> (22 << 24) with code 0. Copied to shared
+// memory by every CTA.
+__device__ uint32_t g_vlc[BS_VLC_ROWS * BS_VLC_COLS];
 // v3 DC delta codes: [0] chroma, [1] luma.
 __constant__ uint32_t c_dcvlc[2 * 512];
 
@@ -69,7 +70,7 @@ __host__ __device__ constexpr uint32_t ymagic_at(int i) {
 void bs_upload_tables() {
 	static uint2 qmagic[64];
 	static uint8_t lenlut[64 * 64];
-	static uint32_t vlc[64 * 64];
+	static uint32_t vlc[BS_VLC_ROWS * BS_VLC_COLS];
 	static uint32_t dcvlc[2 * 512];
 	for (int q = 0; q < 64; q++) {
 		uint32_t d = 2u * (q ? q : 1);
@@ -85,7 +86,8 @@ void bs_upload_tables() {
 			}
 			lenlut[(lv << 6) | run] = (uint8_t)len;
 			uint32_t e = (lv > 0 && run < BS_AC_RUNS && lv < BS_AC_LEVELS) ? BS_AC_VLC[run * BS_AC_LEVELS + lv] : 0;
-			vlc[(lv << 6) | run] = lv == 0 ? 0u : (e ? e : (uint32_t)BS_AC_ESCAPE_BITS << 24);
+			if (lv < BS_VLC_ROWS && run < BS_VLC_COLS)
+				vlc[lv * BS_VLC_COLS + run] = lv == 0 ? 0u : (e ? e : (uint32_t)BS_AC_ESCAPE_BITS << 24);
 		}
 	}
 	for (int i = 0; i < 512; i++) {
@@ -244,7 +246,7 @@ struct PackSmem {
 	uint32_t *gtot;     // per group bit totals -> exclusive group bases
 	uint8_t *grows;     // per plane group: list rows in use (longest list of its 32 blocks), or 0x80: dense rows
 	uint32_t *misc;     // [0..2] rotating frame totals, [3] nonzero AC count, [8..] scan scratch
-	uint32_t *vlc;      // [min(level,63)][run] -> (len<<24)|code, see g_vlc
+	uint32_t *vlc;      // [min(level,41)][min(run,32)] -> (len<<24)|code, see g_vlc
 	uint16_t *lens;     // per block bit length at the current q; after the scan: exclusive offset in its group
 	int16_t *dcval;     // v3: per block quantised DC, replaced in place by its coded delta
 	uint8_t *lenlut;    // [min(level,63)][run] -> code length; preceded by 16 zero guard bytes (see price_entry)
@@ -521,7 +523,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		uint8_t *p = smem_raw;
 		auto take = [&](size_t bytes) { uint8_t *at = p; p += (bytes + 15) & ~(size_t)15; return at; };
 		s.lenlut = take(16 + 64 * 64) + 16;
-		s.vlc = reinterpret_cast<uint32_t *>(take(4 * 64 * 64));
+		s.vlc = reinterpret_cast<uint32_t *>(take(4 * BS_VLC_ROWS * BS_VLC_COLS));
 		s.misc = reinterpret_cast<uint32_t *>(take(4 * (8 + 4 * 32)));
 		s.stream = reinterpret_cast<uint32_t *>(SMEM_STREAM ? take(4 * (size_t)stream_words) : p);
 		s.dctab = reinterpret_cast<uint32_t *>(V3 ? take(4 * 1024) : p);
@@ -546,7 +548,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	for (int i = tid; i < 64 * 64 / 4; i += T)
 		reinterpret_cast<uint32_t *>(s.lenlut)[i] = reinterpret_cast<const uint32_t *>(c_lenlut)[i];
 	if (tid < 4) reinterpret_cast<uint32_t *>(s.lenlut - 16)[tid] = 0;
-	for (int i = tid; i < 64 * 64; i += T) s.vlc[i] = g_vlc[i];
+	for (int i = tid; i < BS_VLC_ROWS * BS_VLC_COLS; i += T) s.vlc[i] = g_vlc[i];
 	if (V3) for (int i = tid; i < 1024; i += T) s.dctab[i] = c_dcvlc[i];
 	for (int i = tid; i < words; i += T) stream[i] = 0;
 	if (tid < 8) s.misc[tid] = 0;
@@ -698,7 +700,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 				const int run = pos - prev - 1;
 				prev = pos;
 				const uint32_t neg = (pos & 32 ? meta.y >> (pos & 31) : meta.x >> pos) & 1u;
-				const uint32_t code = s.vlc[(min(lvl, 63u) << 6) | run];
+				const uint32_t code = s.vlc[min(lvl, (uint32_t)(BS_VLC_ROWS - 1)) * BS_VLC_COLS + min(run, BS_VLC_COLS - 1)];
 				if (code & 0xFFFFFFu) {
 					bw.put((int)(code >> 24), (code & 0xFFFFFFu) | neg);
 				} else {
@@ -772,7 +774,7 @@ size_t bs_pack_smem_bytes(bool v3, bool smem_stream, const BsGeometry &geo, int 
 	size_t n = 0;
 	auto take = [&](size_t bytes) { n += (bytes + 15) & ~(size_t)15; };
 	take(16 + 64 * 64);                   // guard + lenlut
-	take(4 * 64 * 64);                    // vlc
+	take(4 * BS_VLC_ROWS * BS_VLC_COLS);  // vlc
 	take(4 * (8 + 4 * 32));               // misc
 	if (smem_stream) take(4 * (size_t)((max_size_bound + 3) / 4 + 2));
 	if (v3) take(4 * 1024);               // dctab
@@ -856,6 +858,7 @@ cudaError_t bs_launch_pack(int codec, int threads, int min_ctas, int n, const ui
 		if (min_ctas == 3) return launch_pack_cfg<320, 3>(PSXB200_CFG_ARGS);
 		return launch_pack_cfg<320, 2>(PSXB200_CFG_ARGS);
 	}
+	if (threads <= 448 && min_ctas >= 3) return launch_pack_cfg<448, 3>(PSXB200_CFG_ARGS);
 	if (min_ctas >= 2) return launch_pack_cfg<BS_PACK_MAX_THREADS, 2>(PSXB200_CFG_ARGS);
 	return launch_pack_cfg<BS_PACK_MAX_THREADS, 1>(PSXB200_CFG_ARGS);
 #undef PSXB200_CFG_ARGS

@@ -25,6 +25,9 @@ constexpr int BS_META_ROW = 8;
 #define BS_DENSE_MIN 49
 #endif
 constexpr unsigned BS_DENSE_FLAG = 0x100;
+// emit table: rows = levels 0..40 plus one row for everything above, columns = runs 0..31 plus one
+// for everything above; the extra row and column hold the escape marker
+constexpr int BS_VLC_ROWS = 42, BS_VLC_COLS = 33;
 // the bitstream image lives in shared memory while the CTA's total stays below this, else in
 // global memory
 constexpr size_t BS_SMEM_BUDGET = 200 * 1024;

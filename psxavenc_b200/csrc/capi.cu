@@ -71,7 +71,7 @@ size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // ======================================================================================
 
 struct psxb200_bs_encoder {
-	int codec, width, height, fdct, max_batch, host_chunk, pack_threads, pack_min_ctas = 3, sm_count = 0;
+	int codec, width, height, fdct, max_batch, host_chunk, pack_threads, pack_min_ctas = 0 /* 0: by shared-memory fit */, sm_count = 0;
 	bool pack_threads_forced = false;   // PSXB200_PACK_THREADS given: no small-batch override
 	size_t frame_bytes;
 	BsGeometry geo;
@@ -189,11 +189,18 @@ static int bs_encode_chunked(psxb200_bs_encoder *enc, uint4 *d_coefs, int n, con
 		threads = 32 * std::max(1, std::min(BS_PACK_MAX_THREADS / 32, enc->geo.ngroups));
 		min_ctas = 1;
 	}
-	if (bs_pack_smem_bytes(enc->codec != 0, true, enc->geo, max_size_bound, threads) > BS_SMEM_BUDGET) {
+	const size_t smem = bs_pack_smem_bytes(enc->codec != 0, true, enc->geo, max_size_bound, threads);
+	if (smem > BS_SMEM_BUDGET) {
 		gstride = (size_t)(max_size_bound + 3) / 4 + 2;
 		CU_TRY(enc->gstream.reserve(gstride * enc->max_batch));
 		gstream = enc->gstream.ptr;
+	} else if (min_ctas == 0) {
+		// Occupancy beats registers here: four 10-warp CTAs per SM at 48 registers (0.560 ms per
+		// 4096 frames) against three at 64 (0.603 ms) — when four fit the SM's shared memory
+		// (228 KB, 1 KB reserved per CTA); otherwise the 64-register build at three.
+		min_ctas = 4 * (smem + 1024) <= 228 * 1024 ? 4 : 3;
 	}
+	if (min_ctas == 0) min_ctas = 3;
 	for (int first = 0; first < n; first += enc->max_batch) {
 		int m = std::min(enc->max_batch, n - first);
 		if (enc->timing) CU_TRY(enc->mark(stream));
