@@ -38,7 +38,12 @@ def _worker(rank, world, port, queue):
         dist.all_gather_object(outs, d_out.cpu().numpy())
         if rank == 0:
             exp_out, exp_res = oracle.Restated().bs_encode_batch(0, w, h, frames, budgets, oracle.FDCT_ISLOW, stride=18144)
-            queue.put(bool(np.array_equal(all_res.cpu().numpy(), exp_res) and np.array_equal(np.concatenate(outs), exp_out)))
+            got_out = np.concatenate(outs)
+            # only [0, frame_max_size) is the frame's: a failing quant-scale pass of the reference
+            # stores one byte AT frame_max_size before it notices the overflow (mdec.c:323-325)
+            same = all(np.array_equal(got_out[i, :budgets[i]], exp_out[i, :budgets[i]]) and not got_out[i, budgets[i]:].any()
+                       for i in range(n))
+            queue.put(bool(np.array_equal(all_res.cpu().numpy(), exp_res) and same))
         enc.close()
     finally:
         dist.destroy_process_group()
