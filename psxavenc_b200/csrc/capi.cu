@@ -103,9 +103,10 @@ struct psxb200_bs_encoder {
 };
 
 static int bs_pick_threads(const BsGeometry &geo) {
-	// 10 warps per CTA leave 64 registers per thread at 3 CTAs per SM (no spills) and divide the
-	// usual frame sizes' groups of 32 blocks with <= 5 % idle warp slots (320x240: 57 groups in
-	// 6 rounds, 640x480: 225 in 23); measured best on B200 (profiles/r1_sweeps.md).
+	// 10 warps per CTA: four such CTAs fit an SM at 48 registers per thread (three at 64 when the
+	// shared memory does not allow four, see bs_encode_chunked) and the usual frame sizes' groups
+	// of 32 blocks divide with <= 5 % idle warp slots (320x240: 57 groups in 6 rounds, 640x480:
+	// 225 in 23); measured best on B200 (profiles/r1_sweeps.md).
 	const char *env = getenv("PSXB200_PACK_THREADS");
 	if (env && atoi(env) >= 32) return std::min(BS_PACK_MAX_THREADS, atoi(env) / 32 * 32);
 	return 32 * std::max(1, std::min(10, geo.ngroups));
