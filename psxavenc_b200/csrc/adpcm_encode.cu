@@ -8,8 +8,9 @@
 // arg-min, and (b) independent chains (channels / streams), two per warp.
 //
 //   adpcm_spu_kernel   half-warp per SPU stream; 16 output bytes per unit (adpcm.c:356-376)
-//   adpcm_xa_kernel    warp per XA stream (half-warp 0 = left/mono, 1 = right); sound groups
-//                      are assembled in shared memory and stored as one 128-byte row
+//   adpcm_xa_kernel    warp per stereo XA stream (half-warp 0 = left, 1 = right) or per two
+//                      mono streams (one per half-warp); sound groups are assembled in
+//                      shared memory and stored as one 128-byte row
 //                      (encode_block_xa, adpcm.c:193-233; header duplication :321-322)
 //   xa_frame_kernel    sector sync/header/subheader (adpcm.c:266-291, cdrom.c:55-74) and the
 //                      EDC CRC (cdrom.c:30-41, 102-109), one thread per sector
@@ -210,21 +211,25 @@ adpcm_xa_kernel(int n_streams, int stereo, int sector_size, const int16_t *__res
 	constexpr int UNITS = BITS == 4 ? 8 : 4;        // units per 128-byte sound group
 	constexpr int JUMP = BITS == 4 ? 224 : 112;     // interleaved samples per sound group
 	constexpr int WARPS = ADPCM_THREADS / 32;
-	__shared__ uint8_t stage[WARPS][UNITS][32];     // unit codes, one byte per sample
-	__shared__ uint8_t hdrs[WARPS][UNITS];
+	// unit codes, one byte per sample, and unit headers: one set per stream of the warp
+	__shared__ uint8_t stage[WARPS][2][UNITS][32];
+	__shared__ uint8_t hdrs[WARPS][2][UNITS];
 
 	const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4, wslot = threadIdx.x >> 5;
-	const int stream = blockIdx.x * WARPS + wslot;
-	if (stream >= n_streams) return;
+	// stereo: the warp's stream, half-warp 0 drives the left channel, 1 the right one;
+	// mono: each half-warp drives a stream of its own
+	const int warp_id = blockIdx.x * WARPS + wslot;
+	const int stream = stereo ? warp_id : 2 * warp_id + half;
+	const int set = stereo ? 0 : half;              // which stage/hdrs set this half-warp fills
+	if ((stereo ? warp_id : 2 * warp_id) >= n_streams) return;
+	const bool chain = stream < n_streams;          // false: the odd stream out of a mono pair
 
-	const int16_t *base = samples + (long)stream * in_stride;
+	const int16_t *base = samples + (long)(chain ? stream : 0) * in_stride;
 	const int total = stereo ? sample_count * 2 : sample_count;
 	const int groups = ((total + JUMP - 1) / JUMP + 17) / 18 * 18;   // padded to whole sectors (adpcm.c:310)
-	// half-warp 0 drives left/mono, half-warp 1 the right channel (idle when mono)
-	ChannelState st = states[(long)stream * 2 + (stereo ? half : 0)];
+	ChannelState st = states[(long)(chain ? stream : 0) * 2 + (stereo ? half : 0)];
 	int p1 = st.prev1, p2 = st.prev2;
 	unsigned long long mse = st.mse;
-	const bool chain = stereo || half == 0;
 	const int steps = stereo ? UNITS / 2 : UNITS;   // sequential units per chain per group
 
 	// unit (j, step) of this half-warp's chain: source pointer and sample limit. Stereo: the
@@ -252,47 +257,54 @@ adpcm_xa_kernel(int n_streams, int stereo, int sector_size, const int16_t *__res
 			if (chain) {
 				p1 = n1; p2 = n2; mse = m;
 				if (mine) {
-					hdrs[wslot][unit] = (uint8_t)header;
+					hdrs[wslot][set][unit] = (uint8_t)header;
 #pragma unroll
 					for (int i = 0; i < UNIT; i++)
-						stage[wslot][unit][i] = (uint8_t)((codes[(i * BITS) >> 5] >> ((i * BITS) & 31)) & (BITS == 4 ? 0xF : 0xFF));
+						stage[wslot][set][unit][i] = (uint8_t)((codes[(i * BITS) >> 5] >> ((i * BITS) & 31)) & (BITS == 4 ? 0xF : 0xFF));
 				}
 			}
 		}
 		__syncwarp();
-		// assemble the 128-byte sound group: words 0-3 headers (with duplicates), 4-31 data rows
-		uint32_t word;
-		if (lane < 4) {
-			if (BITS == 4) {
-				int h = (lane >> 1) * 4;   // words 0,1 <- units 0-3; words 2,3 <- units 4-7
-				word = hdrs[wslot][h] | (hdrs[wslot][h + 1] << 8) | (hdrs[wslot][h + 2] << 16) | (hdrs[wslot][h + 3] << 24);
+		// assemble the 128-byte sound group(s): words 0-3 headers (with duplicates), 4-31 data rows;
+		// the whole warp stores one group per round — one round when stereo, one per stream when mono
+		for (int g = 0; g < (stereo ? 1 : 2); g++) {
+			const int gstream = stereo ? warp_id : 2 * warp_id + g;
+			if (gstream >= n_streams) break;
+			const uint8_t(*stg)[32] = stage[wslot][g];
+			const uint8_t *hdr = hdrs[wslot][g];
+			uint32_t word;
+			if (lane < 4) {
+				if (BITS == 4) {
+					int h = (lane >> 1) * 4;   // words 0,1 <- units 0-3; words 2,3 <- units 4-7
+					word = hdr[h] | (hdr[h + 1] << 8) | (hdr[h + 2] << 16) | (hdr[h + 3] << 24);
+				} else {
+					// 8-bit: bytes 0-3 = unit headers, copied to 4-7; bytes 8-15 keep the caller's
+					// content in the reference (copied 8-11 -> 12-15, adpcm.c:322) and are
+					// written as zero here (the batch API requires zeroed output buffers).
+					word = lane < 2 ? (hdr[0] | (hdr[1] << 8) | (hdr[2] << 16) | (hdr[3] << 24)) : 0u;
+				}
 			} else {
-				// 8-bit: bytes 0-3 = unit headers, copied to 4-7; bytes 8-15 keep the caller's
-				// content in the reference (copied 8-11 -> 12-15, adpcm.c:322) and are
-				// written as zero here (the batch API requires zeroed output buffers).
-				word = lane < 2 ? (hdrs[wslot][0] | (hdrs[wslot][1] << 8) | (hdrs[wslot][2] << 16) | (hdrs[wslot][3] << 24)) : 0u;
-			}
-		} else {
-			int i = lane - 4;
-			if (BITS == 4) {
-				word = 0;
+				int i = lane - 4;
+				if (BITS == 4) {
+					word = 0;
 #pragma unroll
-				for (int k = 0; k < 4; k++)
-					word |= (uint32_t)(stage[wslot][2 * k][i] | (stage[wslot][2 * k + 1][i] << 4)) << (8 * k);
+					for (int k = 0; k < 4; k++)
+						word |= (uint32_t)(stg[2 * k][i] | (stg[2 * k + 1][i] << 4)) << (8 * k);
+				} else {
+					word = stg[0][i] | (stg[1][i] << 8) | (stg[2][i] << 16) | (stg[3][i] << 24);
+				}
+			}
+			uint8_t *sec = out + (long)gstream * out_stride + (long)(j / 18) * sector_size - (2352 - sector_size);
+			uint8_t *grp = sec + 24 + (j % 18) * 128;
+			if (BITS == 8 && lane >= 2 && lane < 4) {
+				// leave bytes 8-15 of 8-bit groups exactly as the reference does: 12-15 := 8-11
+				if (lane == 3) {
+					uint32_t keep = *reinterpret_cast<const uint32_t *>(grp + 8);
+					*reinterpret_cast<uint32_t *>(grp + 12) = keep;
+				}
 			} else {
-				word = stage[wslot][0][i] | (stage[wslot][1][i] << 8) | (stage[wslot][2][i] << 16) | (stage[wslot][3][i] << 24);
+				*reinterpret_cast<uint32_t *>(grp + 4 * lane) = word;
 			}
-		}
-		uint8_t *sec = out + (long)stream * out_stride + (long)(j / 18) * sector_size - (2352 - sector_size);
-		uint8_t *grp = sec + 24 + (j % 18) * 128;
-		if (BITS == 8 && lane >= 2 && lane < 4) {
-			// leave bytes 8-15 of 8-bit groups exactly as the reference does: 12-15 := 8-11
-			if (lane == 3) {
-				uint32_t keep = *reinterpret_cast<const uint32_t *>(grp + 8);
-				*reinterpret_cast<uint32_t *>(grp + 12) = keep;
-			}
-		} else {
-			*reinterpret_cast<uint32_t *>(grp + 4 * lane) = word;
 		}
 		__syncwarp();
 	}
@@ -381,7 +393,8 @@ cudaError_t adpcm_launch_xa(int n_streams, int format, int stereo, int frequency
 	if (n_streams <= 0 || sectors == 0) return cudaSuccess;
 	int sector_size = format == 0 ? 2336 : 2352;
 	constexpr int WARPS = ADPCM_THREADS / 32;
-	unsigned grid = (unsigned)((n_streams + WARPS - 1) / WARPS);
+	const int warps = stereo ? n_streams : (n_streams + 1) / 2;   // a warp takes two mono streams
+	unsigned grid = (unsigned)((warps + WARPS - 1) / WARPS);
 	if (bits_per_sample == 8)
 		adpcm_xa_kernel<8><<<grid, ADPCM_THREADS, 0, stream>>>(n_streams, stereo, sector_size, d_samples, in_stride,
 		                                                       sample_count, static_cast<ChannelState *>(d_states),

@@ -60,12 +60,6 @@ __host__ __device__ inline int bs_plane_to_block(int pi, int cpad, int nmb) {
 	return li < 4 * nmb ? 6 * (li >> 2) + 2 + (li & 3) : -1;
 }
 
-// Plane index of bitstream-order block b.
-__host__ __device__ inline int bs_block_to_plane(int b, int cpad) {
-	int mb = b / 6, k = b - 6 * mb;
-	return k < 2 ? 2 * mb + k : cpad + 4 * mb + (k - 2);
-}
-
 // STR sector output mode of the pack kernel (encode_sector_str, mdec.c:757-836, driven as
 // encode_file_strspu does for a video-only stream, filefmt.c:546-630). sector_size == 0: off.
 // Frame f of a launch has frame_index K = frame_index0 + f (1-based, mdec.c:769), the byte

@@ -152,3 +152,19 @@ def test_xa_batched_streams(gpu, restated):
         exp = restated.xa_encode(1, True, 37800, 4, 1, 0, st, pcm[s], count, 100)
         assert np.array_equal(out[s], exp), s
         assert bytes(states[s]) == bytes(st)
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+@pytest.mark.parametrize("n", [1, 2, 5])
+def test_xa_batched_mono_streams(gpu, restated, bits, n):
+    """Mono streams share a warp in pairs (one per half-warp): even, odd and single counts."""
+    count = 4032 + 777
+    pad = 224
+    pcm = np.stack([np.concatenate([synth.gen_pcm(count, 1, 70 + s).ravel(), np.zeros(pad, np.int16)]) for s in range(n)])
+    out, states = pb.xa_encode_host(pcm, n, pcm.shape[1], count, fmt=pb.FORMAT_XACD, stereo=False, bits=bits,
+                                    file_number=2, channel_number=3, lba=7)
+    for s in range(n):
+        st = oracle.new_states()
+        exp = restated.xa_encode(1, False, 37800, bits, 2, 3, st, pcm[s], count, 7)
+        assert np.array_equal(out[s], exp), s
+        assert bytes(states[s]) == bytes(st)
