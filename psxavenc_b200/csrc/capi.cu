@@ -98,7 +98,7 @@ struct psxb200_bs_encoder {
 	}
 
 	psxb200_bs_encoder(int c, int w, int h, int f, int mb)
-		: codec(c), width(w), height(h), fdct(f), max_batch(mb), host_chunk(mb < 512 ? mb : 512), pack_threads(320),
+		: codec(c), width(w), height(h), fdct(f), max_batch(mb), host_chunk(mb < 256 ? mb : 256), pack_threads(320),
 		  frame_bytes((size_t)w * h * 3 / 2), geo(w, h) {}
 };
 
