@@ -9,9 +9,16 @@
 
 namespace psxb200 {
 
-constexpr int BS_DCT_THREADS = 128;
+// FDCT kernel CTA: 3 warps divide the usual frames' plane groups exactly (320x240: 57 groups =
+// 19 CTAs, 640x480: 225 = 75) and 9 such CTAs per SM keep the 72-register budget (27 warps);
+// measured: 96 x 9 0.416 ms, 64 x 14 0.416 ms, 128 x 7 0.423 ms per 4096 frames; 128 x 6
+// (80 registers) and 128 x 8 (64 registers, spills) are slower (profiles/r1_sweeps.md).
+#ifndef BS_DCT_THREADS_PER_CTA
+#define BS_DCT_THREADS_PER_CTA 96
+#endif
+constexpr int BS_DCT_THREADS = BS_DCT_THREADS_PER_CTA;
 #ifndef BS_DCT_MIN_CTAS
-#define BS_DCT_MIN_CTAS 7   // 72 registers, 28 warps per SM: measured +7.5 % over 6 (80 registers)
+#define BS_DCT_MIN_CTAS 9
 #endif
 constexpr int BS_PACK_MAX_THREADS = 640;
 // per block in the coefficient plane: up to 8 uint4 rows of list entries ((y << 6) | zig-zag
