@@ -203,17 +203,19 @@ adpcm_spu_kernel(int n_streams, const int16_t *__restrict__ samples, int pitch, 
 
 // ---- XA ----------------------------------------------------------------------------------
 
-template <int BITS>   // 4 or 8
+template <int BITS, bool STEREO>   // 4 or 8 bits per sample; mono and stereo are compiled separately
 __global__ void __launch_bounds__(ADPCM_THREADS, 8)
-adpcm_xa_kernel(int n_streams, int stereo, int sector_size, const int16_t *__restrict__ samples, long in_stride,
+adpcm_xa_kernel(int n_streams, int sector_size, const int16_t *__restrict__ samples, long in_stride,
                 int sample_count, ChannelState *__restrict__ states, uint8_t *__restrict__ out, long out_stride) {
 	constexpr int RANGE = BITS == 4 ? 12 : 8;
 	constexpr int UNITS = BITS == 4 ? 8 : 4;        // units per 128-byte sound group
 	constexpr int JUMP = BITS == 4 ? 224 : 112;     // interleaved samples per sound group
 	constexpr int WARPS = ADPCM_THREADS / 32;
 	// unit codes, one byte per sample, and unit headers: one set per stream of the warp
-	__shared__ uint8_t stage[WARPS][2][UNITS][32];
-	__shared__ uint8_t hdrs[WARPS][2][UNITS];
+	constexpr bool stereo = STEREO;
+	constexpr int SETS = STEREO ? 1 : 2;
+	__shared__ uint8_t stage[WARPS][SETS][UNITS][32];
+	__shared__ uint8_t hdrs[WARPS][SETS][UNITS];
 
 	const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4, wslot = threadIdx.x >> 5;
 	// stereo: the warp's stream, half-warp 0 drives the left channel, 1 the right one;
@@ -267,7 +269,8 @@ adpcm_xa_kernel(int n_streams, int stereo, int sector_size, const int16_t *__res
 		__syncwarp();
 		// assemble the 128-byte sound group(s): words 0-3 headers (with duplicates), 4-31 data rows;
 		// the whole warp stores one group per round — one round when stereo, one per stream when mono
-		for (int g = 0; g < (stereo ? 1 : 2); g++) {
+#pragma unroll
+		for (int g = 0; g < SETS; g++) {
 			const int gstream = stereo ? warp_id : 2 * warp_id + g;
 			if (gstream >= n_streams) break;
 			const uint8_t(*stg)[32] = stage[wslot][g];
@@ -395,14 +398,10 @@ cudaError_t adpcm_launch_xa(int n_streams, int format, int stereo, int frequency
 	constexpr int WARPS = ADPCM_THREADS / 32;
 	const int warps = stereo ? n_streams : (n_streams + 1) / 2;   // a warp takes two mono streams
 	unsigned grid = (unsigned)((warps + WARPS - 1) / WARPS);
-	if (bits_per_sample == 8)
-		adpcm_xa_kernel<8><<<grid, ADPCM_THREADS, 0, stream>>>(n_streams, stereo, sector_size, d_samples, in_stride,
-		                                                       sample_count, static_cast<ChannelState *>(d_states),
-		                                                       d_out, out_stride);
-	else
-		adpcm_xa_kernel<4><<<grid, ADPCM_THREADS, 0, stream>>>(n_streams, stereo, sector_size, d_samples, in_stride,
-		                                                       sample_count, static_cast<ChannelState *>(d_states),
-		                                                       d_out, out_stride);
+	auto kern = bits_per_sample == 8 ? (stereo ? adpcm_xa_kernel<8, true> : adpcm_xa_kernel<8, false>)
+	                                 : (stereo ? adpcm_xa_kernel<4, true> : adpcm_xa_kernel<4, false>);
+	kern<<<grid, ADPCM_THREADS, 0, stream>>>(n_streams, sector_size, d_samples, in_stride, sample_count,
+	                                         static_cast<ChannelState *>(d_states), d_out, out_stride);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess || !frame_sectors) return e;
 	int coding = (stereo ? 1 : 0) | (frequency == 37800 ? 0 : 4) | (bits_per_sample == 8 ? 16 : 0);
