@@ -186,9 +186,18 @@ const char *psxb200_last_error(void);
 
 /* codec: 0 = BS v2, 1 = v3, 2 = v3dc (bs_codec_t). width/height multiples of 16
  * (mdec.c:601-602). max_batch: frames per internal launch (scratch is sized for it).
- * Uses the current CUDA device. NULL on failure. */
+ * The encoder belongs to the CUDA device that is current at creation; every entry point makes
+ * that device current for the duration of the call. NULL on failure. */
 psxb200_bs_encoder_t *psxb200_bs_create(int codec, int width, int height, int fdct_variant, int max_batch);
 void psxb200_bs_destroy(psxb200_bs_encoder_t *enc);
+/* The encoder's CUDA device / the size of one NV21 input frame (1.5 * width * height). */
+int psxb200_bs_device(const psxb200_bs_encoder_t *enc);
+long long psxb200_bs_frame_bytes(const psxb200_bs_encoder_t *enc);
+
+/* Page-locked host memory usable from every device (cudaHostAlloc, portable): host buffers
+ * allocated here are copied from / to directly by the DMA engines. */
+void *psxb200_pinned_alloc(size_t bytes);
+void psxb200_pinned_free(void *p);
 
 /* Device-resident batch: d_frames = n NV21 frames back to back (1.5*W*H bytes each, base
  * 16-byte aligned), d_max_sizes[n] = per-frame byte budgets (frame_max_size), each
@@ -203,9 +212,13 @@ int psxb200_bs_encode_device(psxb200_bs_encoder_t *enc, int n, const uint8_t *d_
                              size_t out_stride, psxb200_bs_result_t *d_results, void *stream);
 
 /* Same with HOST buffers: copies in, encodes and copies out in pipelined chunks on the
- * encoder's own streams; synchronous. Pinned host memory is used in place; pageable memory
- * goes through the driver's staging. Returns the number of frames that failed (0 = all
- * good) or -1 on error. */
+ * encoder's own streams; synchronous. Pinned host memory (psxb200_pinned_alloc, cudaHostAlloc)
+ * is used in place; pageable memory goes through the driver's staging. h_max_sizes[n] is
+ * required (one budget per frame, each <= out_stride). Only the bytes a frame's stream occupies
+ * travel back over the bus; the rest of [0, frame_max_size) is zero-filled on the host (the
+ * reference clears the whole buffer, mdec.c:676), and bytes at and beyond a frame's own
+ * frame_max_size are never written. Returns the number of frames that failed (0 = all good)
+ * or -1 on error. */
 int psxb200_bs_encode_host(psxb200_bs_encoder_t *enc, int n, const uint8_t *h_frames,
                            const int *h_max_sizes, uint8_t *h_out, size_t out_stride,
                            psxb200_bs_result_t *h_results);
@@ -229,6 +242,102 @@ int psxb200_str_encode_host(psxb200_bs_encoder_t *enc, int n, const uint8_t *h_f
                             int first_frame_index, int sectors_num, int sectors_den, int video_id,
                             uint8_t *h_sectors, psxb200_bs_result_t *h_results);
 
+/* The general form of the two calls above: STR / STRCD / STRV video sectors for one or many
+ * independent files, optionally complete (sector framing + EDC) and optionally placed at their
+ * LBA slots of the muxed file image. All fields must be set (memset the struct to 0 first).
+ *
+ *   framing       also write what the reference's mux loop adds around encode_sector_str:
+ *                 init_sector_buffer_video (filefmt.c:73-92: FORMAT_STRCD sync + BCD timecode +
+ *                 mode 2 + doubled subheader, cdrom.c:55-74; FORMAT_STR the doubled subheader)
+ *                 and psx_cdrom_calculate_checksums(.., MODE2_FORM1) (filefmt.c:474,
+ *                 cdrom.c:92-100): EDC of bytes [0x10, 0x818) of the buffer at 0x818. For
+ *                 FORMAT_STR the reference applies that to the 2336-byte buffer, i.e. shifted
+ *                 by 16 bytes against the sector's layout and over 16 bytes it never writes —
+ *                 reproduced as is, over whatever the output buffer holds there.
+ *   interleave    sectors per mux block: 1 = video only, N = one XA audio sector + N-1 video
+ *                 sectors (psx_audio_xa_get_sector_interleave * cd speed, filefmt.c:401-403);
+ *                 trailing_audio = FLAG_STR_TRAILING_AUDIO (filefmt.c:456-461). Decides the
+ *                 LBA (timecode) of each video sector.
+ *   place_at_lba  0: the video sectors of a file follow each other in the output, the first
+ *                 one of the call at byte 0; 1: video sector at LBA a sits at byte
+ *                 (a - lba_origin) * sector_size, audio slots are left alone.
+ *   frames_per_file / file_stride
+ *                 0: all n frames are one file. F: the batch is n / F files of F frames, each
+ *                 starting over at first_frame_index, file f's output at f * file_stride bytes.
+ */
+typedef struct {
+	int format;              /* FORMAT_STR, FORMAT_STRCD or FORMAT_STRV */
+	int first_frame_index;   /* frame_index of a file's first frame in this call, >= 1 (mdec.c:769) */
+	int sectors_num;         /* frame_block_base_overflow (filefmt.c:428) */
+	int sectors_den;         /* frame_block_overflow_den (filefmt.c:429) */
+	int video_id;            /* str_video_id */
+	int framing;
+	int xa_file, xa_channel; /* subheader file / channel (filefmt.c:84-85) */
+	int interleave;
+	int trailing_audio;
+	int place_at_lba;
+	long long lba_origin;
+	int frames_per_file;
+	long long file_stride;   /* bytes, multiple of 4 */
+} psxb200_str_params_t;
+
+/* Slots (sectors) of a file's output region taken by n_frames frames starting at
+ * params->first_frame_index: [*first_slot, *end_slot) relative to byte 0 of the region. */
+int psxb200_str_slot_range(const psxb200_str_params_t *params, int n_frames, long long *first_slot, long long *end_slot);
+int psxb200_str_encode_device_ex(psxb200_bs_encoder_t *enc, int n, const uint8_t *d_frames,
+                                 const psxb200_str_params_t *params, uint8_t *d_sectors,
+                                 psxb200_bs_result_t *d_results, void *stream);
+/* Host buffers; n must be a multiple of frames_per_file when that is set. Bytes of a sector
+ * the reference does not write keep the caller's content. */
+int psxb200_str_encode_host_ex(psxb200_bs_encoder_t *enc, int n, const uint8_t *h_frames,
+                               const psxb200_str_params_t *params, uint8_t *h_sectors,
+                               psxb200_bs_result_t *h_results);
+
+/* encode_file_str (filefmt.c:391-520) on the GPU for n_files independent inputs: file f =
+ * frames_per_file NV21 frames at h_frames + f * frames_per_file * frame_bytes and
+ * samples_per_file XA sample frames (interleaved L,R when stereo) at h_pcm + f * pcm_stride
+ * (int16 units), muxed into the image h_images + f * image_stride: slot s is an XA sector when
+ * s % interleave == 0 (trailing_audio: == interleave - 1), else the file's next video sector;
+ * complete sectors (framing, EDC), frame_index from 1, LBA = slot. params->format, sectors_num,
+ * sectors_den, video_id, xa_file, xa_channel, interleave, trailing_audio are used; h_pcm NULL
+ * or samples_per_file 0: video only (interleave 1). The video and the XA kernels of a group of
+ * files run concurrently on two streams. Bytes neither encoder writes (the ECC area, cdrom.c:98)
+ * are zero; psx_audio_xa_encode_finalize is left to the caller. h_xa_states: n_files
+ * psx_audio_encoder_state_t in/out, or NULL (zero state in, final state dropped).
+ * psxb200_strcd_image_bytes: size of one image. Returns failed frames or -1. */
+long long psxb200_strcd_image_bytes(const psxb200_str_params_t *params, int frames_per_file, int xa_bits, int xa_stereo,
+                                    int samples_per_file);
+int psxb200_strcd_encode_host(psxb200_bs_encoder_t *enc, int n_files, int frames_per_file, const uint8_t *h_frames,
+                              const psxb200_str_params_t *params, int xa_frequency, int xa_bits, int xa_stereo,
+                              const int16_t *h_pcm, long pcm_stride, int samples_per_file, void *h_xa_states,
+                              uint8_t *h_images, long long image_stride, psxb200_bs_result_t *h_results);
+
+/* ---- one process, many devices ----------------------------------------------------------
+ * The reference's host is one single-threaded C process (filefmt.c); these entry points are how
+ * it reaches every GPU of the box: one encoder and one worker thread per device, frames dealt
+ * out in contiguous ranges (they are independent, mdec.c:676-686), every device's results
+ * written straight into the caller's host arrays. No collective is involved. device_ids NULL:
+ * devices 0 .. n_devices-1; n_devices <= 0: all visible devices. Host buffers should be pinned
+ * (psxb200_pinned_alloc). Same contracts and return values as the single-device calls. */
+typedef struct psxb200_bs_multi psxb200_bs_multi_t;
+psxb200_bs_multi_t *psxb200_bs_multi_create(int codec, int width, int height, int fdct_variant, int max_batch,
+                                            int n_devices, const int *device_ids);
+void psxb200_bs_multi_destroy(psxb200_bs_multi_t *m);
+int psxb200_bs_multi_device_count(const psxb200_bs_multi_t *m);
+int psxb200_bs_multi_encode_host(psxb200_bs_multi_t *m, int n, const uint8_t *h_frames, const int *h_max_sizes,
+                                 uint8_t *h_out, size_t out_stride, psxb200_bs_result_t *h_results);
+int psxb200_bs_multi_str_encode_host(psxb200_bs_multi_t *m, int n, const uint8_t *h_frames,
+                                     const psxb200_str_params_t *params, uint8_t *h_sectors,
+                                     psxb200_bs_result_t *h_results);
+int psxb200_bs_multi_strcd_encode_host(psxb200_bs_multi_t *m, int n_files, int frames_per_file, const uint8_t *h_frames,
+                                       const psxb200_str_params_t *params, int xa_frequency, int xa_bits, int xa_stereo,
+                                       const int16_t *h_pcm, long pcm_stride, int samples_per_file, void *h_xa_states,
+                                       uint8_t *h_images, long long image_stride, psxb200_bs_result_t *h_results);
+
+/* Look-ahead statistics of the drop-in encode_sector_str: frames served
+ * from a speculative encode of the frame behind the previous one / frames encoded on demand. */
+void psxb200_bs_lookahead_stats(const psxb200_bs_encoder_t *enc, long long *hits, long long *misses);
+
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 unsigned long long psxb200_launch_count(void);
 
@@ -251,14 +360,23 @@ int psxb200_spu_encode_device(int n_streams, const int16_t *d_samples, int pitch
                               uint8_t *d_out, long out_stride, void *stream);
 int psxb200_spu_encode_host(int n_streams, const int16_t *h_samples, int pitch, long group_stride,
                             int sample_count, void *h_states, uint8_t *h_out, long out_stride);
+/* The same over several devices of this process (see psxb200_bs_multi_*): whole groups of
+ * `pitch` interleaved chains per device when there are at least as many groups as devices
+ * (vagi x B), else chain c on device c mod G (one vagi file; a chain is strictly sequential,
+ * adpcm.c:135-136,186-190, so a single file gains nothing beyond overlap of its channels). */
+int psxb200_spu_encode_host_multi(int n_devices, const int *device_ids, int n_streams, const int16_t *h_samples,
+                                  int pitch, long group_stride, int sample_count, void *h_states, uint8_t *h_out,
+                                  long out_stride);
 
 /* XA-ADPCM, n_streams independent XA streams (adpcm.c:293-332 each, incl. subheaders,
  * sound-group header duplication and EDC). Stream s reads sample_count per-channel frames
  * (interleaved L,R when stereo) at d_samples + s * in_stride (in int16 units; readable up
  * to the end of the last 224/112-sample sound group the reference would touch) and writes
  * sectors of 2336 (format 0) or 2352 (format 1) bytes at d_out + s * out_stride, first
- * sector numbered lba. d_states[n_streams][2] (left, right) in/out. Output buffers must be
- * zero-initialised for format 0 (the reference ORs into the coding byte, adpcm.c:278-288).
+ * sector numbered lba. d_states[n_streams][2] (left, right) in/out. Bytes the reference never
+ * writes keep the buffer's content: the coding byte of format 0 is OR-ed into what is there
+ * (adpcm.c:278-288) and bytes 8-15 of an 8-bit sound group are copied 8-11 -> 12-15 from it
+ * (adpcm.c:322) — start from zeroed buffers for deterministic output, as for the reference.
  * Returns bytes per stream (>= 0) or -1. */
 int psxb200_xa_encode_device(int n_streams, int format, int stereo, int frequency, int bits_per_sample,
                              int file_number, int channel_number, const int16_t *d_samples,
@@ -268,6 +386,18 @@ int psxb200_xa_encode_host(int n_streams, int format, int stereo, int frequency,
                            int file_number, int channel_number, const int16_t *h_samples,
                            long in_stride, int sample_count, int lba, void *h_states,
                            uint8_t *h_out, long out_stride);
+/* psxb200_xa_encode_device with the sectors of a stream sector_stride bytes apart (0: back to
+ * back) and numbered lba + k * lba_step — the XA sectors of a muxed .str image sit in every
+ * interleave-th slot (filefmt.c:456-461, 487-494). */
+int psxb200_xa_encode_device_ex(int n_streams, int format, int stereo, int frequency, int bits_per_sample,
+                                int file_number, int channel_number, const int16_t *d_samples,
+                                long in_stride, int sample_count, int lba, int lba_step, void *d_states,
+                                uint8_t *d_out, long out_stride, long sector_stride, void *stream);
+/* Streams dealt out in contiguous runs over several devices of this process. */
+int psxb200_xa_encode_host_multi(int n_devices, const int *device_ids, int n_streams, int format, int stereo,
+                                 int frequency, int bits_per_sample, int file_number, int channel_number,
+                                 const int16_t *h_samples, long in_stride, int sample_count, int lba, void *h_states,
+                                 uint8_t *h_out, long out_stride);
 
 #ifdef __cplusplus
 }

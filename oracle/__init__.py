@@ -202,6 +202,36 @@ class Reference(_Base):
             self.lib.ref_bs_close(h)
         return out, used, used_per
 
+    def str_mux(self, codec, width, height, frames, fmt=7, pcm=None, n_samples=0, frequency=37800, bits=4, stereo=True,
+                cd_speed=2, fps_num=15, fps_den=1, trailing_audio=False, video_id=0x8001, xa_file=1, xa_channel=0,
+                fdct=FDCT_ISLOW, max_sectors=None):
+        """The sector loop of encode_file_str (filefmt.c:391-520; format 6 = STR, 7 = STRCD) over
+        in-memory frames and PCM -> (image[n_sectors, sector_size] uint8, quant_scale_sum)."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8).reshape(-1, width * height * 3 // 2)
+        n_frames = frames.shape[0]
+        size = 2352 if fmt == 7 else 2336
+        if max_sectors is None:
+            max_sectors = 64 + 16 * n_frames * max(1, (75 * cd_speed * fps_den + fps_num - 1) // fps_num)
+        out = np.zeros((max_sectors, size), dtype=np.uint8)
+        frame_buf = np.zeros(2016 * 64, dtype=np.uint8)
+        qsum = C.c_int(0)
+        if pcm is not None:
+            pcm = np.ascontiguousarray(pcm, dtype=np.int16).ravel()
+            # psx_audio_xa_encode may read a little past the last sample frame (adpcm.c:193-233)
+            pcm = np.concatenate([pcm, np.zeros(512, np.int16)])
+        self.lib.ref_str_mux.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 8 + \
+                                        [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        h = self.lib.ref_bs_open(codec, width, height, self.fdct_mode(fdct))
+        try:
+            n = self.lib.ref_str_mux(h, fmt, video_id, xa_file, xa_channel, frames.ctypes.data, n_frames,
+                                     None if pcm is None else pcm.ctypes.data, n_samples if pcm is not None else 0, frequency,
+                                     bits, int(stereo), cd_speed, fps_num, fps_den, int(trailing_audio), frame_buf.ctypes.data,
+                                     out.ctypes.data, max_sectors, C.byref(qsum))
+        finally:
+            self.lib.ref_bs_close(h)
+        assert n >= 0, "ref_str_mux ran out of room"
+        return out[:n], qsum.value
+
     def spu_encode(self, state, samples, sample_count, pitch, offset=0):
         samples = np.ascontiguousarray(samples, dtype=np.int16).ravel()
         out = np.zeros(16 * ((sample_count + 27) // 28), dtype=np.uint8)

@@ -122,5 +122,86 @@ int ref_str_encode(void *h, int format, int video_id, const uint8_t *frames, int
 	return used;
 }
 
+/* The sector loop of encode_file_str (filefmt.c:391-520) on in-memory inputs, calling the
+ * reference's own encode_sector_str, psx_audio_xa_encode, psx_cdrom_init_sector and
+ * psx_cdrom_calculate_checksums. init_sector_buffer_video is static in filefmt.c (which needs
+ * FFmpeg headers to compile), so its dozen lines (filefmt.c:73-92) are restated here. The
+ * reference's sector buffer is uninitialised stack memory (filefmt.c:453); here every sector
+ * starts zeroed so that the output is deterministic. Runs until all n_frames frames have been
+ * emitted completely; returns the number of sectors written (-1: out of room). audio: n_samples
+ * sample frames per channel (0: no audio stream -> interleave 1, filefmt.c:416-421). */
+int ref_str_mux(void *h, int format, int video_id, int xa_file, int xa_channel, const uint8_t *frames, int n_frames,
+                const int16_t *pcm, int n_samples, int xa_freq, int xa_bits, int xa_stereo, int cd_speed, int fps_num,
+                int fps_den, int trailing_audio, uint8_t *frame_buf, uint8_t *out, int max_sectors, int *quant_scale_sum) {
+	mdec_encoder_t *enc = (mdec_encoder_t *)h;
+	long frame_bytes = (long)enc->video_width * enc->video_height * 3 / 2;
+	psx_audio_xa_settings_t xa;
+	xa.bits_per_sample = xa_bits;
+	xa.frequency = xa_freq;
+	xa.stereo = xa_stereo != 0;
+	xa.file_number = xa_file;
+	xa.channel_number = xa_channel;
+	xa.format = format == FORMAT_STRCD ? PSX_AUDIO_XA_FORMAT_XACD : PSX_AUDIO_XA_FORMAT_XA;
+	int sector_size = psx_audio_xa_get_buffer_size_per_sector(xa);
+	int interleave, audio_samples_per_sector, video_sectors_per_block;
+	if (n_samples > 0) {                                             /* filefmt.c:399-415 */
+		interleave = psx_audio_xa_get_sector_interleave(xa) * cd_speed;
+		audio_samples_per_sector = psx_audio_xa_get_samples_per_sector(xa);
+		video_sectors_per_block = interleave - 1;
+	} else {
+		interleave = 1;
+		audio_samples_per_sector = 0;
+		video_sectors_per_block = 1;
+	}
+	psx_audio_encoder_state_t audio_state;
+	memset(&audio_state, 0, sizeof(audio_state));
+	enc->state.frame_block_base_overflow = (75 * cd_speed) * video_sectors_per_block * fps_den;   /* filefmt.c:428-429 */
+	enc->state.frame_block_overflow_den = interleave * fps_num;
+	enc->state.frame_output = frame_buf;
+	enc->state.frame_index = 0;
+	enc->state.frame_data_offset = 0;
+	enc->state.frame_max_size = 0;
+	enc->state.frame_block_overflow_num = 0;
+	enc->state.quant_scale_sum = 0;
+	int channels = xa_stereo ? 2 : 1;
+	int frames_used = 0, samples_used = 0, sector_count = 0;
+	for (; frames_used < n_frames || enc->state.frame_data_offset < enc->state.frame_max_size; sector_count++) {
+		if (sector_count >= max_sectors) return -1;
+		uint8_t sector[2352];
+		memset(sector, 0, sizeof(sector));
+		int is_video;
+		if (audio_samples_per_sector == 0) is_video = 1;                              /* filefmt.c:456-461 */
+		else if (trailing_audio) is_video = (sector_count % interleave) < video_sectors_per_block;
+		else is_video = (sector_count % interleave) > 0;
+		if (is_video) {
+			psx_cdrom_sector_xa_subheader_t *subheader = NULL;                         /* filefmt.c:73-92 */
+			if (format == FORMAT_STRCD) {
+				psx_cdrom_init_sector((psx_cdrom_sector_t *)sector, sector_count, PSX_CDROM_SECTOR_TYPE_MODE2_FORM1);
+				subheader = ((psx_cdrom_sector_t *)sector)->mode2.subheader;
+			} else if (format == FORMAT_STR) {
+				subheader = (psx_cdrom_sector_xa_subheader_t *)sector;
+			}
+			if (subheader) {
+				subheader->file = xa_file;
+				subheader->channel = xa_channel & PSX_CDROM_SECTOR_XA_CHANNEL_MASK;
+				subheader->submode = PSX_CDROM_SECTOR_XA_SUBMODE_DATA | PSX_CDROM_SECTOR_XA_SUBMODE_RT;
+				subheader->coding = 0;
+				memcpy(subheader + 1, subheader, sizeof(psx_cdrom_sector_xa_subheader_t));
+			}
+			frames_used += encode_sector_str(enc, (format_t)format, (uint16_t)video_id, frames + frames_used * frame_bytes, sector);
+			if (format != FORMAT_STRV)
+				psx_cdrom_calculate_checksums((psx_cdrom_sector_t *)sector, PSX_CDROM_SECTOR_TYPE_MODE2_FORM1);   /* filefmt.c:474 */
+		} else {
+			int samples_length = n_samples - samples_used;                             /* filefmt.c:477-494 */
+			if (samples_length > audio_samples_per_sector) samples_length = audio_samples_per_sector;
+			psx_audio_xa_encode(xa, &audio_state, pcm + (long)samples_used * channels, samples_length, sector_count, sector);
+			samples_used += samples_length;
+		}
+		memcpy(out + (long)sector_count * sector_size, sector, sector_size);
+	}
+	if (quant_scale_sum) *quant_scale_sum = enc->state.quant_scale_sum;
+	return sector_count;
+}
+
 #include <stddef.h>
 size_t ref_sizeof_mdec_encoder(void) { return sizeof(mdec_encoder_t); }

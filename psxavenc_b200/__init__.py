@@ -46,6 +46,20 @@ class XaSettings(C.Structure):
                 ("bits_per_sample", C.c_int), ("file_number", C.c_int), ("channel_number", C.c_int)]
 
 
+class StrParams(C.Structure):
+    """psxb200_str_params_t"""
+    _fields_ = [("format", C.c_int), ("first_frame_index", C.c_int), ("sectors_num", C.c_int), ("sectors_den", C.c_int),
+                ("video_id", C.c_int), ("framing", C.c_int), ("xa_file", C.c_int), ("xa_channel", C.c_int),
+                ("interleave", C.c_int), ("trailing_audio", C.c_int), ("place_at_lba", C.c_int),
+                ("lba_origin", C.c_longlong), ("frames_per_file", C.c_int), ("file_stride", C.c_longlong)]
+
+
+def str_params(fmt, sectors_num, sectors_den, first_frame_index=1, video_id=0x8001, framing=0, xa_file=1, xa_channel=0,
+               interleave=1, trailing_audio=0, place_at_lba=0, lba_origin=0, frames_per_file=0, file_stride=0):
+    return StrParams(fmt, first_frame_index, sectors_num, sectors_den, video_id, framing, xa_file, xa_channel, interleave,
+                     trailing_audio, place_at_lba, lba_origin, frames_per_file, file_stride)
+
+
 class MdecEncoderState(C.Structure):
     """mdec_encoder_state_t (mdec.h:32-55)"""
     _fields_ = [("frame_index", C.c_int), ("frame_data_offset", C.c_int), ("frame_max_size", C.c_int),
@@ -86,6 +100,27 @@ SYMBOLS = {
     "psxb200_launch_count": (C.c_ulonglong, []),
     "psxb200_bs_create": (_P, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "psxb200_bs_destroy": (None, [_P]),
+    "psxb200_bs_device": (C.c_int, [_P]),
+    "psxb200_bs_frame_bytes": (C.c_longlong, [_P]),
+    "psxb200_pinned_alloc": (_P, [C.c_size_t]),
+    "psxb200_pinned_free": (None, [_P]),
+    "psxb200_str_slot_range": (C.c_int, [C.POINTER(StrParams), C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "psxb200_str_encode_device_ex": (C.c_int, [_P, C.c_int, _P, C.POINTER(StrParams), _P, _P, _P]),
+    "psxb200_str_encode_host_ex": (C.c_int, [_P, C.c_int, _P, C.POINTER(StrParams), _P, _P]),
+    "psxb200_strcd_image_bytes": (C.c_longlong, [C.POINTER(StrParams), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "psxb200_strcd_encode_host": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(StrParams), C.c_int, C.c_int, C.c_int,
+                                            _P, C.c_long, C.c_int, _P, _P, C.c_longlong, _P]),
+    "psxb200_bs_multi_create": (_P, [C.c_int] * 6 + [_P]),
+    "psxb200_bs_multi_destroy": (None, [_P]),
+    "psxb200_bs_multi_device_count": (C.c_int, [_P]),
+    "psxb200_bs_multi_encode_host": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "psxb200_bs_multi_str_encode_host": (C.c_int, [_P, C.c_int, _P, C.POINTER(StrParams), _P, _P]),
+    "psxb200_bs_multi_strcd_encode_host": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(StrParams), C.c_int, C.c_int, C.c_int,
+                                                     _P, C.c_long, C.c_int, _P, _P, C.c_longlong, _P]),
+    "psxb200_bs_lookahead_stats": (None, [_P, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "psxb200_spu_encode_host_multi": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int, C.c_long, C.c_int, _P, _P, C.c_long]),
+    "psxb200_xa_encode_device_ex": (C.c_int, [C.c_int] * 7 + [_P, C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, C.c_long, C.c_long, _P]),
+    "psxb200_xa_encode_host_multi": (C.c_int, [C.c_int, _P] + [C.c_int] * 7 + [_P, C.c_long, C.c_int, C.c_int, _P, _P, C.c_long]),
     "psxb200_bs_timing_enable": (None, [_P, C.c_int]),
     "psxb200_bs_timing_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "psxb200_bs_encode_device": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, C.c_size_t, _P, _P]),
@@ -205,6 +240,33 @@ class BsEncoder:
                                              sectors_den, video_id, sectors.ctypes.data, res.ctypes.data), "str_encode_host")
         return sectors, res
 
+    def str_encode_host_ex(self, frames, params, sectors):
+        """psxb200_str_encode_host_ex into the caller's `sectors` array -> res[n, 4] int32."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8).reshape(-1, self.frame_bytes)
+        res = np.zeros((frames.shape[0], 4), dtype=np.int32)
+        _check(lib().psxb200_str_encode_host_ex(self.handle, frames.shape[0], frames.ctypes.data, C.byref(params),
+                                                sectors.ctypes.data, res.ctypes.data), "str_encode_host_ex")
+        return res
+
+    def strcd_encode_host(self, frames, frames_per_file, params, pcm=None, samples_per_file=0, frequency=37800, bits=4,
+                          stereo=True, states=None):
+        """psxb200_strcd_encode_host -> (images[n_files, image_bytes] uint8, res[n, 4] int32)."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8).reshape(-1, self.frame_bytes)
+        n_files = frames.shape[0] // frames_per_file
+        size = int(lib().psxb200_strcd_image_bytes(C.byref(params), frames_per_file, bits, int(stereo),
+                                                   samples_per_file if pcm is not None else 0))
+        images = np.zeros((n_files, size), dtype=np.uint8)
+        res = np.zeros((frames.shape[0], 4), dtype=np.int32)
+        pcm_stride = 0
+        if pcm is not None:
+            pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(n_files, -1)
+            pcm_stride = pcm.shape[1]
+        _check(lib().psxb200_strcd_encode_host(self.handle, n_files, frames_per_file, frames.ctypes.data, C.byref(params),
+                                               frequency, bits, int(stereo), _ptr(pcm), pcm_stride, samples_per_file,
+                                               None if states is None else C.addressof(states), images.ctypes.data, size,
+                                               res.ctypes.data), "strcd_encode_host")
+        return images, res
+
     def encode_host(self, frames, max_sizes, stride=None):
         """frames: uint8 [n, 1.5*W*H]; -> (out[n, stride] uint8, res[n, 4] int32)."""
         frames = np.ascontiguousarray(frames, dtype=np.uint8).reshape(-1, self.frame_bytes)
@@ -215,6 +277,55 @@ class BsEncoder:
         res = np.zeros((n, 4), dtype=np.int32)
         self.encode_host_into(n, frames, max_sizes, out, stride, res)
         return out, res
+
+
+class BsMultiEncoder:
+    """psxb200_bs_multi_*: one process, one encoder + worker thread per device."""
+
+    def __init__(self, codec, width, height, fdct=FDCT_ISLOW, max_batch=256, n_devices=0, device_ids=None):
+        self.frame_bytes = width * height * 3 // 2
+        ids = None
+        if device_ids is not None:
+            ids = (C.c_int * len(device_ids))(*device_ids)
+            n_devices = len(device_ids)
+        self.handle = lib().psxb200_bs_multi_create(codec, width, height, fdct, max_batch, n_devices, ids)
+        if not self.handle:
+            raise Psxb200Error("psxb200_bs_multi_create failed: %s" % last_error())
+        self.n_devices = lib().psxb200_bs_multi_device_count(self.handle)
+
+    def close(self):
+        if self.handle:
+            lib().psxb200_bs_multi_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def encode_host_into(self, n, h_frames, h_max_sizes, h_out, out_stride, h_results):
+        return _check(lib().psxb200_bs_multi_encode_host(self.handle, n, _ptr(h_frames), _ptr(h_max_sizes), _ptr(h_out),
+                                                         out_stride, _ptr(h_results)), "bs_multi_encode_host")
+
+    def str_encode_host_ex(self, frames, params, sectors):
+        frames = np.ascontiguousarray(frames, dtype=np.uint8).reshape(-1, self.frame_bytes)
+        res = np.zeros((frames.shape[0], 4), dtype=np.int32)
+        _check(lib().psxb200_bs_multi_str_encode_host(self.handle, frames.shape[0], frames.ctypes.data, C.byref(params),
+                                                      sectors.ctypes.data, res.ctypes.data), "bs_multi_str_encode_host")
+        return res
+
+
+def spu_encode_host_multi(samples, n_streams, pitch, group_stride, sample_count, n_devices=0, device_ids=None, states=None):
+    """psxb200_spu_encode_host_multi -> (out[n_streams, 16*ceil(count/28)] uint8, states)."""
+    samples = np.ascontiguousarray(samples, dtype=np.int16)
+    if states is None:
+        states = (ChannelState * n_streams)()
+    row = 16 * ((sample_count + 27) // 28)
+    out = np.zeros((n_streams, row), dtype=np.uint8)
+    ids = None
+    if device_ids is not None:
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        n_devices = len(device_ids)
+    _check(lib().psxb200_spu_encode_host_multi(n_devices, ids, n_streams, samples.ctypes.data, pitch, group_stride,
+                                               sample_count, C.addressof(states), out.ctypes.data, row), "spu_encode_host_multi")
+    return out, states
 
 
 def spu_encode_host(samples, n_streams, pitch, group_stride, sample_count, states=None):

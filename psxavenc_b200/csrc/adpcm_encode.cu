@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include "adpcm_encode.h"
+#include "edc.cuh"
 
 namespace psxb200 {
 
@@ -149,12 +150,14 @@ __device__ __forceinline__ void spread_unit(const UnitFetch &f, int (&s)[UNIT]) 
 // ---- SPU ---------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(ADPCM_THREADS, 8)
-adpcm_spu_kernel(int n_streams, const int16_t *__restrict__ samples, int pitch, long group_stride, int sample_count,
-                 const int *__restrict__ counts, ChannelState *__restrict__ states, uint8_t *__restrict__ out,
-                 long out_stride) {
+adpcm_spu_kernel(int n_streams, int stream_first, int stream_step, const int16_t *__restrict__ samples, int pitch,
+                 long group_stride, int sample_count, const int *__restrict__ counts, ChannelState *__restrict__ states,
+                 uint8_t *__restrict__ out, long out_stride) {
 	const int lane = threadIdx.x & 31, sub = lane & 15;
-	const int stream = (int)(((long)blockIdx.x * ADPCM_THREADS + threadIdx.x) >> 4);
-	const bool live = stream < n_streams;
+	// the launch's i-th chain is stream stream_first + i * stream_step of the caller's arrays
+	const int index = (int)(((long)blockIdx.x * ADPCM_THREADS + threadIdx.x) >> 4);
+	const bool live = index < n_streams;
+	const int stream = stream_first + index * stream_step;
 	const int count = live ? (counts ? counts[stream] : sample_count) : 0;
 	const int units = (count + UNIT - 1) / UNIT;
 	// both half-warps of a warp iterate together
@@ -205,7 +208,7 @@ adpcm_spu_kernel(int n_streams, const int16_t *__restrict__ samples, int pitch, 
 
 template <int BITS, bool STEREO>   // 4 or 8 bits per sample; mono and stereo are compiled separately
 __global__ void __launch_bounds__(ADPCM_THREADS, 8)
-adpcm_xa_kernel(int n_streams, int sector_size, const int16_t *__restrict__ samples, long in_stride,
+adpcm_xa_kernel(int n_streams, int sector_size, long sector_stride, const int16_t *__restrict__ samples, long in_stride,
                 int sample_count, ChannelState *__restrict__ states, uint8_t *__restrict__ out, long out_stride) {
 	constexpr int RANGE = BITS == 4 ? 12 : 8;
 	constexpr int UNITS = BITS == 4 ? 8 : 4;        // units per 128-byte sound group
@@ -297,7 +300,7 @@ adpcm_xa_kernel(int n_streams, int sector_size, const int16_t *__restrict__ samp
 					word = stg[0][i] | (stg[1][i] << 8) | (stg[2][i] << 16) | (stg[3][i] << 24);
 				}
 			}
-			uint8_t *sec = out + (long)gstream * out_stride + (long)(j / 18) * sector_size - (2352 - sector_size);
+			uint8_t *sec = out + (long)gstream * out_stride + (long)(j / 18) * sector_stride - (2352 - sector_size);
 			uint8_t *grp = sec + 24 + (j % 18) * 128;
 			if (BITS == 8 && lane >= 2 && lane < 4) {
 				// leave bytes 8-15 of 8-bit groups exactly as the reference does: 12-15 := 8-11
@@ -319,68 +322,78 @@ adpcm_xa_kernel(int n_streams, int sector_size, const int16_t *__restrict__ samp
 
 // ---- XA sector framing + EDC -------------------------------------------------------------
 
-__device__ __forceinline__ uint32_t edc_step(uint32_t crc, uint32_t byte, const uint32_t *tab) {
-	return (crc >> 8) ^ tab[(crc ^ byte) & 0xFF];
-}
+__device__ __forceinline__ uint32_t to_bcd(int v) { return (uint32_t)(v + (v / 10) * 6) & 0xFFu; }
 
-__device__ __forceinline__ uint8_t to_bcd(int v) { return (uint8_t)(v + (v / 10) * 6); }
-
+// One warp per sector: sync/header (XACD only; psx_cdrom_init_sector, cdrom.c:55-74), the
+// doubled subheader (adpcm.c:266-291) and the FORM2 EDC over bytes 0x10..0x92B (cdrom.c:102-109).
 __global__ void __launch_bounds__(128)
-xa_frame_kernel(int n_streams, int sectors_per_stream, int format, int sector_size, int file_number, int channel_number,
-                int coding, int lba, uint8_t *__restrict__ out, long out_stride) {
-	__shared__ uint32_t tab[256];
-	for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-		uint32_t c = (uint32_t)i;
-		for (int b = 0; b < 8; b++) c = (c >> 1) ^ ((c & 1) ? 0xD8018001u : 0u);
-		tab[i] = c;
-	}
+xa_frame_kernel(int n_streams, int sectors_per_stream, int format, int sector_size, long sector_stride, int file_number,
+                int channel_number, int coding, int lba, int lba_step, uint8_t *__restrict__ out, long out_stride,
+                const uint32_t *__restrict__ edc_tab) {
+	__shared__ uint32_t tab[256 + 1024];
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = edc_tab[i];
+	for (int i = threadIdx.x; i < 1024; i += blockDim.x) tab[256 + i] = edc_tab[1280 + i];   // FORM2 advance table
 	__syncthreads();
-	long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const long id = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (id >= (long)n_streams * sectors_per_stream) return;
-	int stream = (int)(id / sectors_per_stream), k = (int)(id - (long)stream * sectors_per_stream);
-	uint8_t *sec = out + (long)stream * out_stride + (long)k * sector_size - (2352 - sector_size);
+	const int stream = (int)(id / sectors_per_stream), k = (int)(id - (long)stream * sectors_per_stream);
+	uint8_t *sec = out + (long)stream * out_stride + (long)k * sector_stride - (2352 - sector_size);
+	uint32_t *sec32 = reinterpret_cast<uint32_t *>(sec);
 
-	uint8_t prior_coding = sec[19];
 	if (format == 1) {
-		int t = lba + k + 150;   // psx_cdrom_init_sector (cdrom.c:55-74)
-		sec[0] = 0;
-		for (int i = 1; i <= 10; i++) sec[i] = 0xFF;
-		sec[11] = 0;
-		sec[12] = to_bcd(t / 4500);
-		sec[13] = to_bcd((t / 75) % 60);
-		sec[14] = to_bcd(t % 75);
-		sec[15] = 2;
-		prior_coding = 0;
+		const int t = lba + k * lba_step + 150;
+		if (lane == 0) sec32[0] = 0xFFFFFF00u;
+		if (lane == 1) sec32[1] = 0xFFFFFFFFu;
+		if (lane == 2) sec32[2] = 0x00FFFFFFu;
+		if (lane == 3) sec32[3] = to_bcd(t / 4500) | (to_bcd((t / 75) % 60) << 8) | (to_bcd(t % 75) << 16) | (2u << 24);
 	}
-	sec[16] = (uint8_t)file_number;
-	sec[17] = (uint8_t)(channel_number & 0x1F);
-	sec[18] = 0x04 | 0x20 | 0x40;                 // AUDIO | FORM2 | RT (adpcm.c:272-275)
-	sec[19] = (uint8_t)(prior_coding | coding);   // OR-ed in the 2336-byte format (adpcm.c:277-288)
-	for (int i = 0; i < 4; i++) sec[20 + i] = sec[16 + i];
-
-	uint32_t crc = 0;                             // cdrom.c:102-109: bytes 0x10 .. 0x92B
-	const uint32_t *w = reinterpret_cast<const uint32_t *>(sec + 0x10);
-	for (int i = 0; i < 0x91C / 4; i++) {
-		uint32_t v = w[i];
-		crc = edc_step(crc, v & 0xFF, tab);
-		crc = edc_step(crc, (v >> 8) & 0xFF, tab);
-		crc = edc_step(crc, (v >> 16) & 0xFF, tab);
-		crc = edc_step(crc, v >> 24, tab);
+	if (lane == 4) {
+		// file, channel & 0x1F, AUDIO | FORM2 | RT (adpcm.c:272-275); the coding byte is OR-ed into
+		// what the buffer holds in the 2336-byte format (adpcm.c:277-288; psx_cdrom_init_sector has
+		// zeroed it in the 2352-byte one)
+		const uint32_t prior = format == 1 ? 0u : (uint32_t)sec[19];
+		const uint32_t sub = (uint32_t)(file_number & 0xFF) | ((uint32_t)(channel_number & 0x1F) << 8) | (0x64u << 16) |
+		                     (((prior | (uint32_t)coding) & 0xFFu) << 24);
+		sec32[4] = sub;
+		sec32[5] = sub;
 	}
-	*reinterpret_cast<uint32_t *>(sec + 0x92C) = crc;
+	__threadfence_block();   // the warp reads its own stores back below
+	__syncwarp();
+	const uint32_t edc = warp_edc<EDC_PIECE_FORM2>(sec32 + 4, 0x91C / 4, tab, tab + 256);
+	if (lane == 0) sec32[0x92C / 4] = edc;
 }
 
 // ---- launchers ---------------------------------------------------------------------------
 
 cudaError_t adpcm_launch_spu(int n_streams, const int16_t *d_samples, int pitch, long group_stride, int sample_count,
-                             const int *d_counts, void *d_states, uint8_t *d_out, long out_stride, cudaStream_t stream) {
+                             const int *d_counts, void *d_states, uint8_t *d_out, long out_stride, cudaStream_t stream,
+                             int stream_first, int stream_step) {
 	if (n_streams <= 0) return cudaSuccess;
 	long threads = (long)n_streams * 16;
 	unsigned grid = (unsigned)((threads + ADPCM_THREADS - 1) / ADPCM_THREADS);
-	adpcm_spu_kernel<<<grid, ADPCM_THREADS, 0, stream>>>(n_streams, d_samples, pitch, group_stride, sample_count,
-	                                                     d_counts, static_cast<ChannelState *>(d_states), d_out,
+	adpcm_spu_kernel<<<grid, ADPCM_THREADS, 0, stream>>>(n_streams, stream_first, stream_step, d_samples, pitch, group_stride,
+	                                                     sample_count, d_counts, static_cast<ChannelState *>(d_states), d_out,
 	                                                     out_stride);
 	return cudaGetLastError();
+}
+
+// Number of int16 elements of `samples` that psx_audio_xa_encode reads (adpcm.c:193-233,
+// 310-319): in stereo the per-unit limit shrinks by 28 while the pointer advances by 56, so
+// the tail group may be read past sample_count*2 (never past its own 224/112 samples).
+long adpcm_xa_input_extent(int stereo, int bits, int sample_count) {
+	const int jump = bits == 8 ? 112 : 224;
+	const int units = bits == 8 ? 4 : 8;
+	const long total = stereo ? 2L * sample_count : sample_count;
+	if (!stereo || total <= 0) return total > 0 ? total : 0;
+	const long j = (total - 1) / jump;   // only the last group holding samples can over-read
+	const long remaining = total - j * jump;
+	long furthest = 0;
+	for (int step = 0; step < units / 2; step++) {
+		long lim = remaining - 28L * step < 28 ? remaining - 28L * step : 28;
+		if (lim > 0 && 56L * step + 2 * lim > furthest) furthest = 56L * step + 2 * lim;
+	}
+	return j * jump + furthest;   // all earlier groups are read completely
 }
 
 int adpcm_xa_sectors(int stereo, int bits_per_sample, int sample_count) {
@@ -391,23 +404,26 @@ int adpcm_xa_sectors(int stereo, int bits_per_sample, int sample_count) {
 
 cudaError_t adpcm_launch_xa(int n_streams, int format, int stereo, int frequency, int bits_per_sample, int file_number,
                             int channel_number, const int16_t *d_samples, long in_stride, int sample_count, int lba,
-                            void *d_states, uint8_t *d_out, long out_stride, bool frame_sectors, cudaStream_t stream) {
+                            int lba_step, void *d_states, uint8_t *d_out, long out_stride, long sector_stride,
+                            const uint32_t *d_edc_tables, cudaStream_t stream) {
 	int sectors = adpcm_xa_sectors(stereo, bits_per_sample, sample_count);
 	if (n_streams <= 0 || sectors == 0) return cudaSuccess;
 	int sector_size = format == 0 ? 2336 : 2352;
+	if (sector_stride <= 0) sector_stride = sector_size;
 	constexpr int WARPS = ADPCM_THREADS / 32;
 	const int warps = stereo ? n_streams : (n_streams + 1) / 2;   // a warp takes two mono streams
 	unsigned grid = (unsigned)((warps + WARPS - 1) / WARPS);
 	auto kern = bits_per_sample == 8 ? (stereo ? adpcm_xa_kernel<8, true> : adpcm_xa_kernel<8, false>)
 	                                 : (stereo ? adpcm_xa_kernel<4, true> : adpcm_xa_kernel<4, false>);
-	kern<<<grid, ADPCM_THREADS, 0, stream>>>(n_streams, sector_size, d_samples, in_stride, sample_count,
+	kern<<<grid, ADPCM_THREADS, 0, stream>>>(n_streams, sector_size, sector_stride, d_samples, in_stride, sample_count,
 	                                         static_cast<ChannelState *>(d_states), d_out, out_stride);
 	cudaError_t e = cudaGetLastError();
-	if (e != cudaSuccess || !frame_sectors) return e;
+	if (e != cudaSuccess || !d_edc_tables) return e;
 	int coding = (stereo ? 1 : 0) | (frequency == 37800 ? 0 : 4) | (bits_per_sample == 8 ? 16 : 0);
 	long n = (long)n_streams * sectors;
-	xa_frame_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n_streams, sectors, format, sector_size, file_number,
-	                                                                  channel_number, coding, lba, d_out, out_stride);
+	xa_frame_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, stream>>>(n_streams, sectors, format, sector_size, sector_stride,
+	                                                                       file_number, channel_number, coding, lba, lba_step,
+	                                                                       d_out, out_stride, d_edc_tables);
 	return cudaGetLastError();
 }
 

@@ -33,8 +33,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "bs_encode.h"
 #include "bs_tables.h"
+#include "edc.cuh"
 #include "fdct.cuh"
 
 namespace psxb200 {
@@ -67,11 +70,26 @@ __host__ __device__ constexpr uint32_t ymagic_at(int i) {
 	return (uint32_t)(0x200000000ull / (unsigned long long)quant_zz_at(i)) + 1u;
 }
 
-void bs_upload_tables() {
+// EDC byte table + advance tables (edc.cuh), see EDC_TABLE_WORDS
+__device__ uint32_t g_edc[EDC_TABLE_WORDS];
+
+constexpr int MAX_DEVICES = 64;
+static std::mutex g_device_lock;          // guards the per-device one-time setup below
+static bool g_tables_uploaded[MAX_DEVICES];
+
+cudaError_t bs_upload_tables() {
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	if (dev < 0 || dev >= MAX_DEVICES) return cudaErrorInvalidDevice;
+	std::lock_guard<std::mutex> guard(g_device_lock);
+	if (g_tables_uploaded[dev]) return cudaSuccess;
+
 	static uint2 qmagic[64];
 	static uint8_t lenlut[64 * 64];
 	static uint32_t vlc[BS_VLC_ROWS * BS_VLC_COLS];
 	static uint32_t dcvlc[2 * 512];
+	static uint32_t edc[EDC_TABLE_WORDS];
 	for (int q = 0; q < 64; q++) {
 		uint32_t d = 2u * (q ? q : 1);
 		qmagic[q].x = (uint32_t)(0x100000000ull / d) + 1;
@@ -94,10 +112,26 @@ void bs_upload_tables() {
 		dcvlc[i] = BS_DC_VLC_CHROMA[i];
 		dcvlc[512 + i] = BS_DC_VLC_LUMA[i];
 	}
-	cudaMemcpyToSymbol(c_qmagic, qmagic, sizeof(qmagic));
-	cudaMemcpyToSymbol(c_lenlut, lenlut, sizeof(lenlut));
-	cudaMemcpyToSymbol(g_vlc, vlc, sizeof(vlc));
-	cudaMemcpyToSymbol(c_dcvlc, dcvlc, sizeof(dcvlc));
+	for (uint32_t i = 0; i < 256; i++) edc[i] = edc_byte_table_entry(i);
+	edc_build_advance_table(edc, EDC_PIECE_FORM1, edc + 256);
+	edc_build_advance_table(edc, EDC_PIECE_FORM2, edc + 1280);
+	// Synchronous copies on the legacy stream, bracketed by device synchronisation: they happen
+	// once per device, before any kernel of this library has been launched on it.
+	if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(c_qmagic, qmagic, sizeof(qmagic))) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(c_lenlut, lenlut, sizeof(lenlut))) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(g_vlc, vlc, sizeof(vlc))) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(c_dcvlc, dcvlc, sizeof(dcvlc))) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(g_edc, edc, sizeof(edc))) != cudaSuccess) return e;
+	if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
+	g_tables_uploaded[dev] = true;
+	return cudaSuccess;
+}
+
+const uint32_t *edc_tables_device() {
+	void *p = nullptr;
+	if (bs_upload_tables() != cudaSuccess || cudaGetSymbolAddress(&p, g_edc) != cudaSuccess) return nullptr;
+	return static_cast<const uint32_t *>(p);
 }
 
 // ---- kernel 1: gather + FDCT -----------------------------------------------------------
@@ -537,12 +571,18 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 
 	const uint4 *fc = coefs + (size_t)f * frame_stride_u4;
 	// STR mode: budget and sector position follow from the frame index alone
-	const long long str_k = (long long)str.frame_index0 + f;
+	const int str_g = str.frame_base + f;                                    // frame of the batch
+	const int str_file = str.frames_per_file > 0 ? str_g / str.frames_per_file : 0;
+	const long long str_k = (long long)str.frame_index0 + (str_g - str_file * str.frames_per_file);
 	const long long str_before = str.sector_size ? (str_k - 1) * str.sectors_num / str.sectors_den : 0;
 	int max_size = str.sector_size ? (int)(str_k * str.sectors_num / str.sectors_den - str_before) * 2016
 	               : max_sizes ? max_sizes[f] : max_size_bound;   // no per-frame budgets: all frames get the bound
 	if (max_size > max_size_bound) max_size = 0;   // contract violation -> frame fails
-	if (str.sector_size) out += (size_t)(str_before - str.sector0) * str.sector_size - (size_t)f * out_stride;
+	if (str.sector_size) out += (size_t)str_file * (size_t)str.file_stride - (size_t)f * out_stride;
+	// sector j of this frame: byte offset of its slot in the file's output region
+	auto str_sector = [&](int j) -> uint8_t * {
+		return out + (size_t)f * out_stride + (size_t)(bs_str_slot(str, str_before + j) - str.slot0) * str.sector_size;
+	};
 	const int words = max_size > 0 ? (max_size + 3) / 4 + 2 : 0;
 
 	for (int i = tid; i < 64 * 64 / 4; i += T)
@@ -614,15 +654,13 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	auto word_at = [&](int i) -> uint32_t * {
 		if (!str.sector_size) return out32 + i;
 		int j = i / 504;
-		return reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(out32) + (size_t)j * str.sector_size +
-		                                    str.header_offset + 32) + (i - 504 * j);
+		return reinterpret_cast<uint32_t *>(str_sector(j) + str.header_offset + 32) + (i - 504 * j);
 	};
 	// STR sector headers (mdec.c:782-820)
 	auto write_str_headers = [&](uint32_t bytes_used, uint32_t bs0, uint32_t bs1) {
 		const int chunks = max_size / 2016;
 		for (int j = tid; j < chunks; j += T) {
-			uint32_t *h = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(out32) + (size_t)j * str.sector_size +
-			                                           str.header_offset);
+			uint32_t *h = reinterpret_cast<uint32_t *>(str_sector(j) + str.header_offset);
 			h[0] = 0x0160u | ((uint32_t)(str.video_id & 0xFFFF) << 16);
 			h[1] = (uint32_t)j | ((uint32_t)chunks << 16);
 			h[2] = (uint32_t)str_k;
@@ -814,11 +852,22 @@ static cudaError_t launch_pack_t(int threads, size_t smem, int n, const uint4 *d
                                  psxb200_bs_result_t *d_results, uint32_t *d_gstream, size_t gstream_stride,
                                  const BsStrLayout &str, cudaStream_t stream) {
 	auto kern = bs_pack_kernel<V3, SMEM_STREAM, MAX_THREADS, MIN_CTAS>;
-	static size_t configured = 0;
-	if (smem > configured) {
-		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	// The opt-in to more than 48 KB of dynamic shared memory is a per-device attribute of this
+	// instantiation: raised to the hardware maximum once per device.
+	static bool configured[MAX_DEVICES];
+	{
+		int dev = 0;
+		cudaError_t e = cudaGetDevice(&dev);
 		if (e != cudaSuccess) return e;
-		configured = smem;
+		if (dev < 0 || dev >= MAX_DEVICES) return cudaErrorInvalidDevice;
+		std::lock_guard<std::mutex> guard(g_device_lock);
+		if (!configured[dev]) {
+			int optin = 0;
+			e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+			if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+			if (e != cudaSuccess) return e;
+			configured[dev] = true;
+		}
 	}
 	kern<<<n, threads, smem, stream>>>(d_coefs, geo.frame_stride_u4, geo.nblk, geo.ngroups, geo.nsgroups,
 	                                   geo.cgroups * 32, geo.nmb, codec,
@@ -862,6 +911,64 @@ cudaError_t bs_launch_pack(int codec, int threads, int min_ctas, int n, const ui
 	if (min_ctas >= 2) return launch_pack_cfg<BS_PACK_MAX_THREADS, 2>(PSXB200_CFG_ARGS);
 	return launch_pack_cfg<BS_PACK_MAX_THREADS, 1>(PSXB200_CFG_ARGS);
 #undef PSXB200_CFG_ARGS
+}
+
+// ---- STR mode: sector framing + FORM1 EDC ------------------------------------------------
+//
+// One warp per (frame, sector of the frame). Writes what init_sector_buffer_video puts into a
+// video sector before encode_sector_str runs (filefmt.c:73-92: for FORMAT_STRCD sync, BCD
+// timecode of the sector's LBA, mode 2 and the doubled subheader, cdrom.c:55-74; for FORMAT_STR
+// the doubled subheader at offset 0) and then what psx_cdrom_calculate_checksums(.., FORM1)
+// does to the buffer it is handed (filefmt.c:474, cdrom.c:92-100): the EDC of bytes
+// [0x10, 0x818) stored at 0x818. For FORMAT_STR that buffer is the 2336-byte sector itself, so the
+// range is shifted by 16 bytes against the sector's real layout and covers 16 bytes the encoder
+// never writes — reproduced as is (those bytes are whatever the output buffer held).
+__global__ void __launch_bounds__(256)
+str_frame_kernel(int n_frames, int max_chunks, uint8_t *__restrict__ out, const uint32_t *__restrict__ edc_tab, const BsStrLayout str) {
+	__shared__ uint32_t tab[256 + 1024];
+	for (int i = threadIdx.x; i < 256 + 1024; i += blockDim.x) tab[i] = edc_tab[i];   // byte table + FORM1 advance table
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (w >= (long long)n_frames * max_chunks) return;
+	const int f = (int)(w / max_chunks), j = (int)(w - (long long)f * max_chunks);
+	const int g = str.frame_base + f;
+	const int file = str.frames_per_file > 0 ? g / str.frames_per_file : 0;
+	const long long k = (long long)str.frame_index0 + (g - file * str.frames_per_file);
+	const long long before = (k - 1) * str.sectors_num / str.sectors_den;
+	const int chunks = (int)(k * str.sectors_num / str.sectors_den - before);
+	if (j >= chunks) return;
+	const long long v = before + j;
+	uint8_t *sec = out + (size_t)file * (size_t)str.file_stride + (size_t)(bs_str_slot(str, v) - str.slot0) * str.sector_size;
+	uint32_t *sec32 = reinterpret_cast<uint32_t *>(sec);
+
+	// subheader: file, channel & 0x1F, DATA | RT, coding 0 (filefmt.c:84-87)
+	const uint32_t sub = (uint32_t)(str.xa_file & 0xFF) | ((uint32_t)(str.xa_channel & 0x1F) << 8) | (0x48u << 16);
+	if (str.format == FORMAT_STRCD) {
+		const int t = (int)bs_str_lba(str, v) + 150;
+		auto bcd = [](int x) { return (uint32_t)(x + (x / 10) * 6) & 0xFFu; };
+		if (lane == 0) sec32[0] = 0xFFFFFF00u;
+		if (lane == 1) sec32[1] = 0xFFFFFFFFu;
+		if (lane == 2) sec32[2] = 0x00FFFFFFu;
+		if (lane == 3) sec32[3] = bcd(t / 4500) | (bcd((t / 75) % 60) << 8) | (bcd(t % 75) << 16) | (2u << 24);
+		if (lane == 4 || lane == 5) sec32[lane] = sub;
+	} else {
+		if (lane < 2) sec32[lane] = sub;
+	}
+	__threadfence_block();   // the warp reads its own stores back below
+	__syncwarp();
+	const uint32_t edc = warp_edc<EDC_PIECE_FORM1>(sec32 + 4, 0x808 / 4, tab, tab + 256);
+	if (lane == 0) sec32[0x818 / 4] = edc;
+}
+
+cudaError_t bs_launch_str_framing(int n, int max_chunks, uint8_t *d_out, const BsStrLayout &str, cudaStream_t stream) {
+	if (n <= 0 || max_chunks <= 0 || str.format == FORMAT_STRV) return cudaSuccess;
+	const uint32_t *tab = edc_tables_device();
+	if (!tab) return cudaErrorInitializationError;
+	const long long warps = (long long)n * max_chunks;
+	const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+	str_frame_kernel<<<grid, 256, 0, stream>>>(n, max_chunks, d_out, tab, str);
+	return cudaGetLastError();
 }
 
 }  // namespace psxb200

@@ -68,21 +68,48 @@ __host__ __device__ inline int bs_plane_to_block(int pi, int cpad, int nmb) {
 }
 
 // STR sector output mode of the pack kernel (encode_sector_str, mdec.c:757-836, driven as
-// encode_file_strspu does for a video-only stream, filefmt.c:546-630). sector_size == 0: off.
-// Frame f of a launch has frame_index K = frame_index0 + f (1-based, mdec.c:769), the byte
-// budget 2016 * (floor(K*num/den) - floor((K-1)*num/den)) (mdec.c:772-774 in closed form) and
-// its sectors start at sector floor((K-1)*num/den) - sector0 of the output buffer.
+// encode_file_str / encode_file_strspu do, filefmt.c:391-520, 546-630). sector_size == 0: off.
+// A launch covers frames [frame_base, frame_base + n) of a batch that holds one or more
+// independent files of frames_per_file frames each (0: the whole batch is one file). Frame k of
+// a file has frame_index K = frame_index0 + k (1-based, mdec.c:769), the byte budget
+// 2016 * (floor(K*num/den) - floor((K-1)*num/den)) (mdec.c:772-774 in closed form) and its
+// sectors are the file's video sectors v = floor((K-1)*num/den) + j. Video sector v sits in slot
+// v of the file's output region, or — place_at_lba — in the slot of its LBA in the muxed file
+// (one XA audio sector per `interleave` sectors, filefmt.c:456-461); slot0 is the slot that maps
+// to byte 0 of the region.
 struct BsStrLayout {
-	int sector_size;        // bytes between consecutive sectors
+	int sector_size;        // bytes between consecutive slots
 	int header_offset;      // offset of the 32-byte STR header inside a sector (mdec.c:824-829)
-	int frame_index0;       // frame_index of the launch's first frame
+	int frame_index0;       // frame_index of a file's first frame in this batch
 	int sectors_num;        // frame_block_base_overflow
 	int sectors_den;        // frame_block_overflow_den
-	long long sector0;      // floor((first frame_index of the batch - 1) * num / den)
 	int video_id, width, height;
+	int frame_base;         // batch index of the launch's first frame
+	int frames_per_file;    // 0: one file
+	long long file_stride;  // bytes between the output regions of consecutive files
+	int interleave;         // 1: video only; N: 1 audio + N-1 video sectors per block
+	int audio_first;        // the audio sector opens the block (default) / closes it (FLAG_STR_TRAILING_AUDIO)
+	int place_at_lba;
+	long long slot0;
+	int framing;            // also write what init_sector_buffer_video + FORM1 checksums write (filefmt.c:73-92, 474)
+	int xa_file, xa_channel;
+	int format;             // FORMAT_STR / FORMAT_STRCD / FORMAT_STRV
 };
 
-void bs_upload_tables();
+// LBA of video sector v of a file (filefmt.c:456-461 with a constant video_sectors_per_block)
+__host__ __device__ inline long long bs_str_lba(const BsStrLayout &l, long long v) {
+	if (l.interleave <= 1) return v;
+	return v + v / (l.interleave - 1) + (l.audio_first ? 1 : 0);
+}
+__host__ __device__ inline long long bs_str_slot(const BsStrLayout &l, long long v) {
+	return l.place_at_lba ? bs_str_lba(l, v) : v;
+}
+
+// EDC tables (edc.cuh) of the current device:
+const uint32_t *edc_tables_device();   // device pointer to the tables of the current device (after bs_upload_tables)
+
+// uploads the constant tables to the current device (once per device; thread-safe)
+cudaError_t bs_upload_tables();
 size_t bs_pack_smem_bytes(bool v3, bool smem_stream, const BsGeometry &geo, int max_size_bound, int threads);
 
 cudaError_t bs_launch_dct(int fdct_variant, const uint8_t *d_frames, size_t frame_bytes, int n, int width, int height,
@@ -93,5 +120,9 @@ cudaError_t bs_launch_pack(int codec, int threads, int min_ctas, int n, const ui
                            const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
                            psxb200_bs_result_t *d_results, uint32_t *d_gstream, size_t gstream_stride,
                            const BsStrLayout &str, cudaStream_t stream);
+
+// STR mode, framing: sync/header/subheader of the video sectors and their FORM1 EDC
+// (filefmt.c:73-92, cdrom.c:55-74, 92-100), after bs_launch_pack wrote headers and payloads.
+cudaError_t bs_launch_str_framing(int n, int max_chunks, uint8_t *d_out, const BsStrLayout &str, cudaStream_t stream);
 
 }  // namespace psxb200

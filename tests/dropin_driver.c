@@ -21,7 +21,7 @@ static void *slurp(const char *path, long *size) {
 	fseek(f, 0, SEEK_END);
 	*size = ftell(f);
 	fseek(f, 0, SEEK_SET);
-	void *p = malloc(*size + 64);
+	void *p = calloc(1, *size + (4 << 20));   /* slack behind the data: the decoder's frame queue has a spare slot (decoding.c:448-451) */
 	if (fread(p, 1, *size, f) != (size_t)*size) exit(2);
 	fclose(f);
 	return p;

@@ -114,6 +114,8 @@ def _mux_strcd(lib, frames, pcm, n_sectors, w, h):
     enc.state.quant_scale_sum = 0
     audio_state = pb.EncoderState()
     out = np.zeros((n_sectors, 2352), np.uint8)
+    # one spare slot behind the frames, as in the decoder's queue (decoding.c:448-451)
+    frames = np.concatenate([frames, np.zeros((1, frames.shape[1]), np.uint8)])
     frame_pos, sample_pos = 0, 0
     for s in range(n_sectors):
         if s % interleave > 0:       # video sector (filefmt.c:458-461)
