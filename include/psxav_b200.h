@@ -399,6 +399,28 @@ int psxb200_xa_encode_host_multi(int n_devices, const int *device_ids, int n_str
                                  const int16_t *h_samples, long in_stride, int sample_count, int lba, void *h_states,
                                  uint8_t *h_out, long out_stride);
 
+/* ---- front end: decoded pictures -> NV21 --------------------------
+ * What the reference's decoder does with libswscale before the encoder sees a frame
+ * (psxavenc/decoding.c:286-311, 463-475): bicubic scaling to the encoder's size and conversion
+ * to full-range BT.601 NV21 (Y plane + interleaved Cr,Cb plane). DEVICE pointers only — the
+ * point is to feed frames that are already in HBM (a decoder's output) without a PCIe round
+ * trip; a host RGB source would double the bytes per frame on the link the host entry points
+ * are bound by. Same filter structure as libswscale's (cubic B=0 C=0.6 stretched by the scale
+ * ratio, chroma of RGB pixel pairs averaged first, edges replicated; an unscaled YUV420P source
+ * is re-interleaved without range conversion, as libswscale does), evaluated in float32:
+ * results match libswscale within +-1 per sample (tests/test_gpu_color.py), not bit for bit.
+ *
+ * d_src: n pictures src_frame_stride bytes apart. RGB24/BGR24/RGBA/BGRA: packed rows of src_pitch
+ * bytes. YUV420P: Y plane (src_pitch x src_height), then U and V planes (src_pitch/2 x
+ * src_height/2); src_full_range 0 = limited ("MPEG") range, expanded to full range. d_frames:
+ * n NV21 frames of 1.5 * dst_width * dst_height bytes. d_scratch: psxb200_nv21_scratch_bytes
+ * bytes, 8-byte aligned. Asynchronous on `stream`. Returns 0 / -1. */
+enum { PSXB200_PIX_RGB24 = 0, PSXB200_PIX_BGR24 = 1, PSXB200_PIX_RGBA = 2, PSXB200_PIX_BGRA = 3, PSXB200_PIX_YUV420P = 4 };
+size_t psxb200_nv21_scratch_bytes(int pixfmt, int n, int src_width, int src_height, int dst_width);
+int psxb200_nv21_from_device(int pixfmt, int src_full_range, int n, const uint8_t *d_src, size_t src_frame_stride,
+                             int src_width, int src_height, int src_pitch, int dst_width, int dst_height,
+                             uint8_t *d_frames, void *d_scratch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

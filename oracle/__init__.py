@@ -246,6 +246,9 @@ class Reference(_Base):
         samples = np.ascontiguousarray(samples, dtype=np.int16).ravel()
         if out is None:
             out = np.zeros(self.xa_buffer_size(fmt, stereo, bits, sample_count), dtype=np.uint8)
+        # (re)state the prototype: tests that drive this library through other struct classes reset it
+        self.lib.psx_audio_xa_encode.argtypes = [XaSettingsRef, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        self.lib.psx_audio_xa_encode_finalize.argtypes = [XaSettingsRef, C.c_void_p, C.c_int]
         n = self.lib.psx_audio_xa_encode(cfg, C.byref(states), samples.ctypes.data, sample_count, lba,
                                          out.ctypes.data)
         if finalize:

@@ -22,6 +22,7 @@ LIB_PATH = os.environ.get("PSXB200_LIB") or os.path.join(HERE, "libpsxav_b200.so
 FDCT_ISLOW, FDCT_SSE2 = 0, 1
 CODEC_V2, CODEC_V3, CODEC_V3DC = 0, 1, 2
 FORMAT_XA, FORMAT_XACD, FORMAT_STR, FORMAT_STRCD, FORMAT_STRV, FORMAT_SBS = 0, 1, 6, 7, 9, 10
+PIX_RGB24, PIX_BGR24, PIX_RGBA, PIX_BGRA, PIX_YUV420P = 0, 1, 2, 3, 4
 
 
 class BsResult(C.Structure):
@@ -117,6 +118,8 @@ SYMBOLS = {
     "psxb200_bs_multi_str_encode_host": (C.c_int, [_P, C.c_int, _P, C.POINTER(StrParams), _P, _P]),
     "psxb200_bs_multi_strcd_encode_host": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(StrParams), C.c_int, C.c_int, C.c_int,
                                                      _P, C.c_long, C.c_int, _P, _P, C.c_longlong, _P]),
+    "psxb200_nv21_scratch_bytes": (C.c_size_t, [C.c_int] * 5),
+    "psxb200_nv21_from_device": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_size_t] + [C.c_int] * 5 + [_P, _P, _P]),
     "psxb200_bs_lookahead_stats": (None, [_P, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "psxb200_spu_encode_host_multi": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int, C.c_long, C.c_int, _P, _P, C.c_long]),
     "psxb200_xa_encode_device_ex": (C.c_int, [C.c_int] * 7 + [_P, C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, C.c_long, C.c_long, _P]),

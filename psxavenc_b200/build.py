@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpsxav_b200.so")
-SOURCES = ["bs_encode.cu", "adpcm_encode.cu", "capi_bs.cu", "capi_audio.cu", "capi_multi.cu"]
+SOURCES = ["bs_encode.cu", "adpcm_encode.cu", "color_convert.cu", "capi_bs.cu", "capi_audio.cu", "capi_multi.cu", "capi_color.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CFLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -538,7 +538,22 @@ __device__ __forceinline__ int quant_dc(uint32_t mag, uint32_t negative) {
 	return max(-0x200, min(0x1FE, d));
 }
 
-template <bool V3, bool SMEM_STREAM, int MAX_THREADS, int MIN_CTAS>
+// STR mode: where frame f of the launch sits in its file (see BsStrLayout)
+struct StrFrame {
+	long long k;        // frame_index (1-based)
+	long long before;   // video sectors of the file before this frame
+	int file;
+};
+__device__ __forceinline__ StrFrame str_frame(const BsStrLayout &str, int f) {
+	const int g = str.frame_base + f;
+	StrFrame sf;
+	sf.file = str.frames_per_file > 0 ? g / str.frames_per_file : 0;
+	sf.k = (long long)str.frame_index0 + (g - sf.file * str.frames_per_file);
+	sf.before = (sf.k - 1) * str.sectors_num / str.sectors_den;
+	return sf;
+}
+
+template <bool V3, bool SMEM_STREAM, bool STR, int MAX_THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS)
 bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk, int ngroups, int nsgroups, int cpad,
                int nmb, int codec,
@@ -570,19 +585,16 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	uint32_t *stream = SMEM_STREAM ? s.stream : gstream + (size_t)f * gstream_stride;
 
 	const uint4 *fc = coefs + (size_t)f * frame_stride_u4;
-	// STR mode: budget and sector position follow from the frame index alone
-	const int str_g = str.frame_base + f;                                    // frame of the batch
-	const int str_file = str.frames_per_file > 0 ? str_g / str.frames_per_file : 0;
-	const long long str_k = (long long)str.frame_index0 + (str_g - str_file * str.frames_per_file);
-	const long long str_before = str.sector_size ? (str_k - 1) * str.sectors_num / str.sectors_den : 0;
-	int max_size = str.sector_size ? (int)(str_k * str.sectors_num / str.sectors_den - str_before) * 2016
-	               : max_sizes ? max_sizes[f] : max_size_bound;   // no per-frame budgets: all frames get the bound
+	// STR mode: the budget follows from the frame index alone (the sector positions are worked out
+	// again after the search: nothing of this stays live across it)
+	int max_size;
+	if (STR) {
+		const StrFrame sf = str_frame(str, f);
+		max_size = (int)(sf.k * str.sectors_num / str.sectors_den - sf.before) * 2016;
+	} else {
+		max_size = max_sizes ? max_sizes[f] : max_size_bound;   // no per-frame budgets: all frames get the bound
+	}
 	if (max_size > max_size_bound) max_size = 0;   // contract violation -> frame fails
-	if (str.sector_size) out += (size_t)str_file * (size_t)str.file_stride - (size_t)f * out_stride;
-	// sector j of this frame: byte offset of its slot in the file's output region
-	auto str_sector = [&](int j) -> uint8_t * {
-		return out + (size_t)f * out_stride + (size_t)(bs_str_slot(str, str_before + j) - str.slot0) * str.sector_size;
-	};
 	const int words = max_size > 0 ? (max_size + 3) / 4 + 2 : 0;
 
 	for (int i = tid; i < 64 * 64 / 4; i += T)
@@ -649,10 +661,15 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	}
 
 	uint32_t *out32 = reinterpret_cast<uint32_t *>(out + (size_t)f * out_stride);
+	const StrFrame sf = STR ? str_frame(str, f) : StrFrame{0, 0, 0};
+	// sector j of this frame: its slot in the file's output region
+	auto str_sector = [&](int j) -> uint8_t * {
+		return out + (size_t)sf.file * (size_t)str.file_stride + (size_t)(bs_str_slot(str, sf.before + j) - str.slot0) * str.sector_size;
+	};
 	// destination of 32-bit word i of the frame's bitstream buffer: contiguous, or sliced into
 	// 2016-byte sector payloads behind their 32-byte headers (mdec.c:831-832)
 	auto word_at = [&](int i) -> uint32_t * {
-		if (!str.sector_size) return out32 + i;
+		if (!STR) return out32 + i;
 		int j = i / 504;
 		return reinterpret_cast<uint32_t *>(str_sector(j) + str.header_offset + 32) + (i - 504 * j);
 	};
@@ -663,7 +680,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 			uint32_t *h = reinterpret_cast<uint32_t *>(str_sector(j) + str.header_offset);
 			h[0] = 0x0160u | ((uint32_t)(str.video_id & 0xFFFF) << 16);
 			h[1] = (uint32_t)j | ((uint32_t)chunks << 16);
-			h[2] = (uint32_t)str_k;
+			h[2] = (uint32_t)sf.k;
 			h[3] = bytes_used;
 			h[4] = (uint32_t)(str.width & 0xFFFF) | ((uint32_t)(str.height & 0xFFFF) << 16);
 			h[5] = bs0;
@@ -673,7 +690,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	};
 	if (q >= 64) {
 		for (int i = tid; i < (max_size >> 2); i += T) *word_at(i) = 0;
-		if (!str.sector_size)
+		if (!STR)
 			for (int i = (max_size & ~3) + tid; i < max_size; i += T) out[(size_t)f * out_stride + i] = 0;
 		else
 			write_str_headers(0, 0, 0);
@@ -795,8 +812,8 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		else { uint32_t x = stream[i - 2]; v = (x >> 16) | (x << 16); }
 		*word_at(i) = v;
 	}
-	if (str.sector_size) write_str_headers((uint32_t)((8 + 2 * units + 3) & ~3), hdr0, hdr1);
-	if (!str.sector_size && tid < (max_size & 3)) {
+	if (STR) write_str_headers((uint32_t)((8 + 2 * units + 3) & ~3), hdr0, hdr1);
+	if (!STR && tid < (max_size & 3)) {
 		int i = (max_size & ~3) + tid;   // >= 8 here, since the frame fitted
 		uint32_t x = stream[(i >> 2) - 2];
 		uint32_t v = (x >> 16) | (x << 16);
@@ -846,12 +863,12 @@ cudaError_t bs_launch_dct(int fdct_variant, const uint8_t *d_frames, size_t fram
 	return cudaGetLastError();
 }
 
-template <bool V3, bool SMEM_STREAM, int MAX_THREADS, int MIN_CTAS>
+template <bool V3, bool SMEM_STREAM, bool STR, int MAX_THREADS, int MIN_CTAS>
 static cudaError_t launch_pack_t(int threads, size_t smem, int n, const uint4 *d_coefs, const BsGeometry &geo, int codec,
                                  const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
                                  psxb200_bs_result_t *d_results, uint32_t *d_gstream, size_t gstream_stride,
                                  const BsStrLayout &str, cudaStream_t stream) {
-	auto kern = bs_pack_kernel<V3, SMEM_STREAM, MAX_THREADS, MIN_CTAS>;
+	auto kern = bs_pack_kernel<V3, SMEM_STREAM, STR, MAX_THREADS, MIN_CTAS>;
 	// The opt-in to more than 48 KB of dynamic shared memory is a per-device attribute of this
 	// instantiation: raised to the hardware maximum once per device.
 	static bool configured[MAX_DEVICES];
@@ -884,11 +901,18 @@ static cudaError_t launch_pack_cfg(bool v3, bool smem_stream, int threads, size_
                                    cudaStream_t stream) {
 #define PSXB200_PACK_ARGS threads, smem, n, d_coefs, geo, codec, d_max_sizes, max_size_bound, d_out, out_stride, \
 	d_results, d_gstream, gstream_stride, str, stream
+	if (str.sector_size) {
+		if (v3)
+			return smem_stream ? launch_pack_t<true, true, true, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
+			                   : launch_pack_t<true, false, true, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
+		return smem_stream ? launch_pack_t<false, true, true, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
+		                   : launch_pack_t<false, false, true, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
+	}
 	if (v3)
-		return smem_stream ? launch_pack_t<true, true, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
-		                   : launch_pack_t<true, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
-	return smem_stream ? launch_pack_t<false, true, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
-	                   : launch_pack_t<false, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
+		return smem_stream ? launch_pack_t<true, true, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
+		                   : launch_pack_t<true, false, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
+	return smem_stream ? launch_pack_t<false, true, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
+	                   : launch_pack_t<false, false, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
 #undef PSXB200_PACK_ARGS
 }
 

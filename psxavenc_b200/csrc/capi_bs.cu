@@ -122,6 +122,12 @@ extern "C" void psxb200_bs_destroy(psxb200_bs_encoder_t *enc) {
 			cudaStreamDestroy(s.stream);
 		}
 		if (s.res_ready) cudaEventDestroy(s.res_ready);
+		if (s.audio_stream) {
+			cudaStreamSynchronize(s.audio_stream);
+			cudaStreamDestroy(s.audio_stream);
+		}
+		if (s.audio_done) cudaEventDestroy(s.audio_done);
+		if (s.image_ready) cudaEventDestroy(s.image_ready);
 		s.coefs.release();
 		s.gstream.release();
 		s.in.release();
@@ -148,12 +154,6 @@ extern "C" void psxb200_bs_destroy(psxb200_bs_encoder_t *enc) {
 	a.res.release();
 	a.coefs.release();
 	a.gstream.release();
-	if (enc->audio_stream) {
-		cudaStreamSynchronize(enc->audio_stream);
-		cudaStreamDestroy(enc->audio_stream);
-	}
-	if (enc->audio_done) cudaEventDestroy(enc->audio_done);
-	if (enc->image_ready) cudaEventDestroy(enc->image_ready);
 	for (cudaEvent_t e : enc->events) cudaEventDestroy(e);
 	delete enc;
 }
@@ -649,9 +649,11 @@ extern "C" int psxb200_strcd_encode_host(psxb200_bs_encoder_t *enc, int n_files,
 	CU_TRY(guard.status);
 	for (BsSlot &s : enc->slots)
 		if (slot_prepare(enc, s)) return -1;
-	if (!enc->audio_stream) CU_TRY(cudaStreamCreateWithFlags(&enc->audio_stream, cudaStreamNonBlocking));
-	if (!enc->audio_done) CU_TRY(cudaEventCreateWithFlags(&enc->audio_done, cudaEventDisableTiming));
-	if (!enc->image_ready) CU_TRY(cudaEventCreateWithFlags(&enc->image_ready, cudaEventDisableTiming));
+	for (BsSlot &s : enc->slots) {
+		if (!s.audio_stream) CU_TRY(cudaStreamCreateWithFlags(&s.audio_stream, cudaStreamNonBlocking));
+		if (!s.audio_done) CU_TRY(cudaEventCreateWithFlags(&s.audio_done, cudaEventDisableTiming));
+		if (!s.image_ready) CU_TRY(cudaEventCreateWithFlags(&s.image_ready, cudaEventDisableTiming));
+	}
 	const uint32_t *edc = edc_tables_device();
 	if (!edc) return fail("psxb200_strcd_encode_host: EDC tables unavailable");
 
@@ -671,7 +673,10 @@ extern "C" int psxb200_strcd_encode_host(psxb200_bs_encoder_t *enc, int n_files,
 	const long pcm_extent = audio ? adpcm_xa_input_extent(xa_stereo, xa_bits, samples_per_file) : 0;
 	const long pcm_dev_stride = (long)round_up((size_t)pcm_extent + 224, 8);   // zero tail: the last sound group may read past the end
 
-	const int group = std::max(1, std::min(n_files, enc->host_chunk / frames_per_file));
+	// Files per chunk: a chunk's XA chains take their full serial latency (72 units per sector and
+	// channel) however few files it holds, so chunks are made large enough — four host chunks,
+	// 1024 frames by default — for the copies of the next chunk to cover it.
+	const int group = std::max(1, std::min(n_files, 4 * enc->host_chunk / frames_per_file));
 	const int bound = str_max_budget(batch);
 	struct Pending { int file0, files; };
 	Pending pending[BS_SLOTS] = {};
@@ -701,16 +706,16 @@ extern "C" int psxb200_strcd_encode_host(psxb200_bs_encoder_t *enc, int n_files,
 		CU_TRY(s.h_res.reserve((size_t)group * frames_per_file));
 		// the image starts out zeroed: both encoders leave some bytes alone
 		CU_TRY(cudaMemsetAsync(s.out.ptr, 0, dev_stride * files, s.stream));
-		CU_TRY(cudaEventRecord(enc->image_ready, s.stream));
+		CU_TRY(cudaEventRecord(s.image_ready, s.stream));
 		CU_TRY(cudaMemcpyAsync(s.in.ptr, h_frames + (size_t)file0 * frames_per_file * enc->frame_bytes, (size_t)m * enc->frame_bytes,
 		                       cudaMemcpyHostToDevice, s.stream));
 		if (audio) {
 			// XA chains of this group on the audio stream, concurrent with the video kernels
-			cudaStream_t as = enc->audio_stream;
+			cudaStream_t as = s.audio_stream;
 			CU_TRY(s.pcm.reserve((size_t)group * pcm_dev_stride));
 			CU_TRY(s.states.reserve((size_t)group * 48));
 			CU_TRY(s.h_states.reserve((size_t)group * 48));
-			CU_TRY(cudaStreamWaitEvent(as, enc->image_ready, 0));
+			CU_TRY(cudaStreamWaitEvent(as, s.image_ready, 0));
 			CU_TRY(cudaMemsetAsync(s.pcm.ptr, 0, (size_t)files * pcm_dev_stride * sizeof(int16_t), as));
 			CU_TRY(cudaMemcpy2DAsync(s.pcm.ptr, (size_t)pcm_dev_stride * 2, h_pcm + (size_t)file0 * pcm_stride,
 			                         (size_t)(files > 1 ? pcm_stride : pcm_extent) * 2, (size_t)pcm_extent * 2, files,
@@ -728,13 +733,13 @@ extern "C" int psxb200_strcd_encode_host(psxb200_bs_encoder_t *enc, int n_files,
 			                       (long)dev_stride, (long)batch.interleave * ss, edc, as));
 			g_launches += 2;
 			CU_TRY(cudaMemcpyAsync(s.h_states.ptr, s.states.ptr, (size_t)files * 48, cudaMemcpyDeviceToHost, as));
-			CU_TRY(cudaEventRecord(enc->audio_done, as));
+			CU_TRY(cudaEventRecord(s.audio_done, as));
 		}
 		BsStrLayout l = batch;
 		l.file_stride = (long long)dev_stride;
 		l.slot0 = 0;
 		if (bs_encode_chunked(enc, s.coefs, s.gstream, m, s.in.ptr, nullptr, bound, s.out.ptr, 0, s.res.ptr, s.stream, &l)) return -1;
-		if (audio) CU_TRY(cudaStreamWaitEvent(s.stream, enc->audio_done, 0));
+		if (audio) CU_TRY(cudaStreamWaitEvent(s.stream, s.audio_done, 0));
 		CU_TRY(cudaMemcpy2DAsync(h_images + (size_t)file0 * (size_t)image_stride, files > 1 ? (size_t)image_stride : image_bytes,
 		                         s.out.ptr, dev_stride, image_bytes, files, cudaMemcpyDeviceToHost, s.stream));
 		CU_TRY(cudaMemcpyAsync(s.h_res.ptr, s.res.ptr, (size_t)m * sizeof(psxb200_bs_result_t), cudaMemcpyDeviceToHost, s.stream));

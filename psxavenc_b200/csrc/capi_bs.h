@@ -23,7 +23,10 @@ struct BsSlot {
 	psxb200::DeviceBuffer<int> sizes;
 	psxb200::DeviceBuffer<psxb200_bs_result_t> res;
 	psxb200::PinnedBuffer<psxb200_bs_result_t> h_res;
-	// psxb200_strcd_encode_host: the chunk's XA input and channel states
+	// psxb200_strcd_encode_host: the chunk's XA chains run beside its video kernels on a stream of
+	// their own (XA chains of different chunks overlap as well: a chain is latency-bound)
+	cudaStream_t audio_stream = nullptr;
+	cudaEvent_t audio_done = nullptr, image_ready = nullptr;
 	psxb200::DeviceBuffer<int16_t> pcm;
 	psxb200::DeviceBuffer<uint8_t> states;
 	psxb200::PinnedBuffer<uint8_t> h_states;
@@ -55,8 +58,6 @@ struct psxb200_bs_encoder {
 	psxb200::DeviceBuffer<uint32_t> gstream;
 	BsSlot slots[BS_SLOTS];
 	BsLookahead ahead;
-	cudaStream_t audio_stream = nullptr;            // psxb200_strcd_encode_host: XA beside the video
-	cudaEvent_t audio_done = nullptr, image_ready = nullptr;
 	// optional per-kernel timing (psxb200_bs_timing_*): three events per internal launch pair
 	bool timing = false;
 	std::vector<cudaEvent_t> events;

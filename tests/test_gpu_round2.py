@@ -117,10 +117,10 @@ def test_strcd_file_images(reference, fmt, trailing):
     .str image (video sectors with budgets 16128,18144,18144,... + one 37800 Hz 4-bit stereo XA
     sector per 8, both produced concurrently) for several files at once; each image must equal
     what the reference's encode_file_str loop writes for that file."""
-    w, h, fpf, n_files = 320, 240, 6, 3
+    w, h, fpf, n_files = 320, 240, 6, 7
     interleave = 8
-    enc = pb.BsEncoder(0, w, h, pb.FDCT_ISLOW, max_batch=8)      # 1 file per group -> 3 groups over the slots
-    frames = np.concatenate([_strcd_case(fpf, 10 * f, noise=2 + f) for f in range(n_files)])
+    enc = pb.BsEncoder(0, w, h, pb.FDCT_ISLOW, max_batch=3)      # 2 files per group -> 4 groups over the 3 slots
+    frames = np.concatenate([_strcd_case(fpf, 10 * f, noise=2 + f % 3) for f in range(n_files)])
     params = pb.str_params(fmt, 150 * (interleave - 1), 15 * interleave, interleave=interleave, trailing_audio=int(trailing),
                            xa_file=1, xa_channel=2)
     # how many sectors the video takes decides how much audio the mux loop consumes
