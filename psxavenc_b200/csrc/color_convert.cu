@@ -6,8 +6,7 @@
 // PCIe link the host entry points are bound by.
 //
 // The filter structure follows libswscale's (probed on the libswscale 9.1 binary in this image;
-// restated in numpy in oracle/color_model.py, which tests/test_color_model.py pins against the
-// binary's outputs):
+// the tests carry a numpy restatement of it that is pinned against the binary's outputs):
 // RGB sources are converted to YCbCr per source pixel, chroma of horizontally adjacent pixel
 // pairs is averaged first (chrSrcW = ceil(W/2)); luma is resampled src -> dst and chroma
 // (chrSrcW x srcH for RGB, W/2 x H/2 for YUV420P) -> dst/2 x dst/2 with the Mitchell-Netravali
