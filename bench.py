@@ -255,10 +255,14 @@ class Ctx:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         self.dist = None
+        self.host_group = None
         if self.world > 1:
             import torch.distributed as dist
             dist.init_process_group("nccl", device_id=self.dev)
             self.dist = dist
+            # a second, CPU-side group: ranks that wait on it leave their GPU idle (an NCCL barrier
+            # parks a spinning kernel on it), which the single-process multi-device leg needs
+            self.host_group = dist.new_group(backend="gloo")
         self.stream = torch.cuda.current_stream()
         self.fdct = fdct_from_name(args.fdct)
         self.peak, self.peak_src = load_peak()
@@ -268,6 +272,11 @@ class Ctx:
         if self.dist:
             self.dist.barrier()
         self.torch.cuda.synchronize()
+
+    def host_barrier(self):
+        self.torch.cuda.synchronize()
+        if self.host_group is not None:
+            self.dist.barrier(group=self.host_group)
 
     def max_over_ranks(self, values):
         t = self.torch.tensor(list(values), dtype=self.torch.float64, device=self.dev)
@@ -370,8 +379,6 @@ def bench_headline(ctx, line):
         step()
     drain()
     ctx.barrier()
-    enc.timing(True)
-    enc.read_timing()
 
     sampler = ClockSampler(ctx.local) if ctx.rank == 0 else None
     launches0 = pb.launch_count()
@@ -385,12 +392,20 @@ def bench_headline(ctx, line):
     ctx.barrier()
     elapsed_ms = a.elapsed_time(b)
     launches = pb.launch_count() - launches0
-    dct_ms, pack_ms, pairs = enc.read_timing()
-    enc.timing(False)
 
     # the same loop for at least a second: sustained clocks
     sus_ms, sus_passes = ctx.timed(lambda: (step(), drain()), args.steps, min_seconds=1.0)
     clocks = sampler.stop() if sampler else None
+
+    # per-kernel durations: a few more steps with every launch bracketed by CUDA events on its
+    # stream (the library then issues the launches of a step back to back on one stream)
+    enc.timing(True)
+    enc.read_timing()
+    for _ in range(5):
+        leg.step()
+    torch.cuda.synchronize()
+    dct_ms, pack_ms, pairs = enc.read_timing()
+    enc.timing(False)
 
     # ---- parity spot check against the CPU oracle on this run's own bytes (every rank) --------
     import oracle
@@ -446,13 +461,13 @@ def bench_headline(ctx, line):
     # ---- e2e through ONE process driving all GPUs (rank 0; the others wait) -------------------
     single = None
     if ctx.world > 1 and pb.device_count() >= ctx.world:
-        ctx.barrier()
+        ctx.host_barrier()
         if ctx.rank == 0:
             try:
                 single = e2e_single_process(ctx, wl, h_frames.numpy(), res, h_out.numpy())
             except Exception as e:      # keep the per-rank number if the single-process leg cannot run
                 single = {"error": str(e)}
-        ctx.barrier()
+        ctx.host_barrier()
 
     if ctx.rank == 0:
         world = ctx.world
@@ -466,7 +481,7 @@ def bench_headline(ctx, line):
             gbs = algo * frames_per_launch / (ms / 1000.0) / 1e9 if ms > 0 else 0.0
             per_kernel[name] = {"algorithmic_bytes_per_launch": algo * frames_per_launch, "launch_ms": ms, "gbs": gbs,
                                 "frac": gbs / ctx.peak, "traffic": traffic.get(name),
-                                "share_of_step": ms * (n // frames_per_launch) / step_ms if step_ms else None}
+                                "share_of_kernel_time": ms * pairs / (dct_ms + pack_ms) if dct_ms + pack_ms else None}
         whole = wl.algo_bytes * n / (step_ms / 1000.0) / 1e9
         e2e_value = world * n * e2e_steps / (e2e_ms / 1000.0)
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * wl.frame_bytes,
@@ -487,6 +502,8 @@ def bench_headline(ctx, line):
             "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "fdct": args.fdct, "frames_per_launch": frames_per_launch,
+                       "launch_pipeline": "launches of a step alternate between two forked streams" if n > frames_per_launch
+                       and os.environ.get("PSXB200_DEVICE_PIPELINE", "1") != "0" else "one stream",
                        "l2": "inputs larger than L2 (%.0f MB of frames per step per GPU)" % (n * wl.frame_bytes / 1e6),
                        "quant_scale_mean": float(res[:, 2].mean()), "parity_spot_check": True,
                        "collective": "all_gather of per-frame results on a side stream" if world > 1 else "none"},
@@ -497,7 +514,7 @@ def bench_headline(ctx, line):
                          "traffic": (traffic.get("bs_dct_kernel") or 0) + (traffic.get("bs_pack_kernel") or 0) or None,
                          "peak_source": ctx.peak_src, "algorithmic_bytes_per_launch": wl.algo_bytes * frames_per_launch,
                          "algorithmic_bytes_per_frame": wl.algo_bytes, "step_ms": step_ms,
-                         "per_kernel": per_kernel, "kernel_ms_total": dct_ms + pack_ms, "step_ms_total": elapsed_ms,
+                         "per_kernel": per_kernel, "kernel_ms_per_step_serial": (dct_ms + pack_ms) / 5, "step_ms_total": elapsed_ms,
                          "note": "integer-issue bound kernels (ncu: profiles/r2_*): the HBM fraction is reported, not the limiter"},
             "e2e": e2e,
             "gpu_launches": int(launches),

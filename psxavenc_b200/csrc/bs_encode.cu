@@ -538,6 +538,72 @@ __device__ __forceinline__ int quant_dc(uint32_t mag, uint32_t negative) {
 	return max(-0x200, min(0x1FE, d));
 }
 
+// ---- census: skipping quant scales that provably cannot fit ------------------------------
+//
+// The reference takes the first quant scale whose stream fits, trying q = 1, 2, ... in turn
+// (mdec.c:663-722); skipping a q is only allowed when it is certain to fail. Every coefficient
+// that is nonzero at q costs at least the run-0 code of its level (the shortest code of a level,
+// and lengths grow with the level), so  fixed + sum over entries of len(level(y, q), run 0)  is a
+// lower bound of the frame's bit total at q; capping y at 15 only lowers it further. One walk over
+// the lists builds a histogram of min(y, 15) — per-thread 16-bit counters in the (still zero)
+// bitstream image, so no two threads ever touch the same counter (a thread sees at most
+// 64 * ceil(groups / warps) <= 1536 entries) — from which the bound follows for all q at once. Called by all threads of the CTA; returns the smallest q >= 2 the bound cannot exclude
+// (64: none) and leaves `bins` zeroed again.
+constexpr int CENSUS_BINS = 15;
+
+__device__ __noinline__ int census_first_candidate(const uint4 *__restrict__ fc, int ngroups, int cpad, int nmb,
+                                                   const uint8_t *grows, uint16_t *bins, const uint8_t *lenlut,
+                                                   uint32_t *scratch /* >= 64 words */, int fixed_bits, int limit_bits) {
+	const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+	uint16_t *mine = bins + tid;
+	auto count = [&](uint32_t y) {
+		if (y) mine[(min(y, (uint32_t)CENSUS_BINS) - 1) * T]++;
+	};
+	for (int g = ngroups - 1 - wid; g >= 0; g -= nw) {
+		if (bs_plane_to_block(g * 32 + lane, cpad, nmb) < 0) continue;
+		const uint4 *gp = fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane;
+		const int rows = grows[g];
+		const bool dense = rows & 0x80;
+		const int nrows = dense ? 8 : rows;
+		for (int r = 0; r < nrows; r++) {
+			const uint4 w = gp[r * 32];
+			const uint32_t v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+			for (int t = 0; t < 4; t++) {
+				// dense rows hold bare y values, list rows (y << 6) | position
+				count(dense ? v[t] & 0xFFFFu : (v[t] & 0xFFFFu) >> 6);
+				count(dense ? v[t] >> 16 : v[t] >> 22);
+			}
+		}
+	}
+	__syncthreads();
+	if (tid < 64) scratch[tid] = tid == CENSUS_BINS ? 64u : 0u;   // [0..14] bin totals, [15] the answer
+	__syncthreads();
+	for (int b = wid; b < CENSUS_BINS; b += nw) {
+		uint32_t sum = 0;
+		for (int i = lane; i < T; i += 32) {
+			sum += bins[b * T + i];
+			bins[b * T + i] = 0;
+		}
+		sum = warp_sum(sum);
+		if (lane == 0) scratch[b] = sum;
+	}
+	__syncthreads();
+	if (tid >= 2 && tid < 64) {
+		const uint32_t q = (uint32_t)tid;
+		long long bound = fixed_bits;
+		for (int b = 0; b < CENSUS_BINS; b++) {
+			const uint32_t level = ((uint32_t)(b + 1) + q) / (2 * q);
+			if (level) bound += (long long)scratch[b] * lenlut[min(level, 63u) << 6];
+		}
+		if (bound <= (long long)limit_bits) atomicMin(&scratch[CENSUS_BINS], q);
+	}
+	__syncthreads();
+	const int first = (int)scratch[CENSUS_BINS];
+	__syncthreads();
+	return first;
+}
+
 // STR mode: where frame f of the launch sits in its file (see BsStrLayout)
 struct StrFrame {
 	long long k;        // frame_index (1-based)
@@ -629,6 +695,8 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	// pass whose running total passes it has failed (the reference's writer overflows at that
 	// point too, mdec.c:323-325) and is abandoned early.
 	const int limit_bits = max_size >= 8 ? 16 * ((max_size - 8) >> 1) - 10 : -1;
+	// the census needs CENSUS_BINS counters per thread in the (zeroed) shared-memory image
+	const bool census_possible = SMEM_STREAM && 2 * words >= CENSUS_BINS * T;
 	int q = 1;
 	uint32_t total_bits = 0;
 	for (; q < 64; q++) {
@@ -636,6 +704,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		// the (usually busier) luma groups at the high end of the plane go first; drawing groups
 		// from a shared ticket counter instead of this static round-robin measured no better
 		uint32_t *total = &s.misc[q % 3];
+		int visited = 0;
 		for (int g = ngroups - 1 - wid; g >= 0; g -= nw) {
 			const int b = bs_plane_to_block(g * 32 + lane, cpad, nmb);
 			int bits = 0;
@@ -646,18 +715,30 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 				bits += 2 + (V3 ? (int)(dc_code(b) >> 24) : 10);
 				s.lens[b] = (uint16_t)bits;
 			}
+			visited++;
 			const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)bits);
 			uint32_t before = 0;
 			if (lane == 0) before = atomicAdd(total, sum);
 			before = __shfl_sync(0xFFFFFFFFu, before, 0);
 			if ((int)(before + sum) > limit_bits) break;
 		}
+		if (q == 1 && lane == 0) atomicAdd(&s.misc[4], (uint32_t)visited);
 		__syncthreads();
 		total_bits = *total;
 		if (tid == 0) s.misc[(q + 2) % 3] = 0;
 		// stream = blocks + 10-bit end-of-frame code; byte budget rule of flush_bits
 		int units = (int)((total_bits + 10 + 15) >> 4);
 		if (8 + 2 * units <= max_size) break;
+		// The first pass ran over its budget before it had seen half of the frame: the content is
+		// far too busy for the small quant scales. Rule the hopeless ones out in one go.
+		if (q == 1 && census_possible && 2 * (int)s.misc[4] < ngroups) {
+			// v2: 10-bit DC + 2-bit end of block per block; v3: DC codes are at least 2 bits long
+			const int first = census_first_candidate(fc, ngroups, cpad, nmb, s.grows, reinterpret_cast<uint16_t *>(s.stream), s.lenlut, s.misc + 8,
+			                                         nblk * (V3 ? 4 : 12), limit_bits);
+			if (tid < 3) s.misc[tid] = 0;
+			__syncthreads();
+			q = max(q, first - 1);   // the loop moves on to `first`
+		}
 	}
 
 	uint32_t *out32 = reinterpret_cast<uint32_t *>(out + (size_t)f * out_stride);

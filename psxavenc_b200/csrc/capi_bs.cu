@@ -101,6 +101,7 @@ extern "C" psxb200_bs_encoder_t *psxb200_bs_create(int codec, int width, int hei
 	cudaError_t e = cudaGetDevice(&enc->device);
 	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&enc->sm_count, cudaDevAttrMultiProcessorCount, enc->device);
 	if (const char *env = getenv("PSXB200_PACK_MIN_CTAS")) enc->pack_min_ctas = atoi(env);
+	if (const char *env = getenv("PSXB200_DEVICE_PIPELINE")) enc->device_pipeline = atoi(env);
 	if (const char *env = getenv("PSXB200_HOST_CHUNK")) enc->host_chunk = std::max(1, std::min(max_batch, atoi(env)));
 	if (e == cudaSuccess) e = bs_upload_tables();
 	if (e == cudaSuccess) e = enc->coefs.reserve((size_t)max_batch * enc->geo.frame_stride_u4);
@@ -141,6 +142,16 @@ extern "C" void psxb200_bs_destroy(psxb200_bs_encoder_t *enc) {
 	}
 	enc->coefs.release();
 	enc->gstream.release();
+	enc->coefs2.release();
+	enc->gstream2.release();
+	for (int i = 0; i < 2; i++) {
+		if (enc->pipe[i]) {
+			cudaStreamSynchronize(enc->pipe[i]);
+			cudaStreamDestroy(enc->pipe[i]);
+		}
+		if (enc->pipe_join[i]) cudaEventDestroy(enc->pipe_join[i]);
+	}
+	if (enc->pipe_fork) cudaEventDestroy(enc->pipe_fork);
 	BsLookahead &a = enc->ahead;
 	if (a.stream) {
 		cudaStreamSynchronize(a.stream);
@@ -251,8 +262,31 @@ extern "C" int psxb200_bs_encode_device(psxb200_bs_encoder_t *enc, int n, const 
 		return fail("psxb200_bs_encode_device: alignment/stride contract violated");
 	DeviceGuard guard(enc->device);
 	CU_TRY(guard.status);
-	return bs_encode_chunked(enc, enc->coefs, enc->gstream, n, d_frames, d_max_sizes, max_size_bound, d_out, out_stride,
-	                         d_results, static_cast<cudaStream_t>(stream));
+	cudaStream_t user = static_cast<cudaStream_t>(stream);
+	if (!enc->device_pipeline || n <= enc->max_batch || enc->timing)
+		return bs_encode_chunked(enc, enc->coefs, enc->gstream, n, d_frames, d_max_sizes, max_size_bound, d_out, out_stride,
+		                         d_results, user);
+	// several launches: alternate them between two forked streams (see psxb200_bs_encoder::pipe)
+	for (int i = 0; i < 2; i++) {
+		if (!enc->pipe[i]) CU_TRY(cudaStreamCreateWithFlags(&enc->pipe[i], cudaStreamNonBlocking));
+		if (!enc->pipe_join[i]) CU_TRY(cudaEventCreateWithFlags(&enc->pipe_join[i], cudaEventDisableTiming));
+	}
+	if (!enc->pipe_fork) CU_TRY(cudaEventCreateWithFlags(&enc->pipe_fork, cudaEventDisableTiming));
+	CU_TRY(cudaEventRecord(enc->pipe_fork, user));
+	for (int i = 0; i < 2; i++) CU_TRY(cudaStreamWaitEvent(enc->pipe[i], enc->pipe_fork, 0));
+	int k = 0;
+	for (int first = 0; first < n; first += enc->max_batch, k ^= 1) {
+		const int m = std::min(enc->max_batch, n - first);
+		if (bs_encode_chunked(enc, k ? enc->coefs2 : enc->coefs, k ? enc->gstream2 : enc->gstream, m,
+		                      d_frames + (size_t)first * enc->frame_bytes, d_max_sizes ? d_max_sizes + first : nullptr, max_size_bound,
+		                      d_out + (size_t)first * out_stride, out_stride, d_results + first, enc->pipe[k]))
+			return -1;
+	}
+	for (int i = 0; i < 2; i++) {
+		CU_TRY(cudaEventRecord(enc->pipe_join[i], enc->pipe[i]));
+		CU_TRY(cudaStreamWaitEvent(user, enc->pipe_join[i], 0));
+	}
+	return 0;
 }
 
 // ---- host pipeline ----------------------------------------------------------------------

@@ -56,6 +56,16 @@ struct psxb200_bs_encoder {
 	// scratch of the device-pointer entry points (they run on the caller's stream)
 	psxb200::DeviceBuffer<uint4> coefs;
 	psxb200::DeviceBuffer<uint32_t> gstream;
+	// device-pointer entry points, batches of more than one launch: the launches alternate
+	// between two internal streams forked from (and joined back into) the caller's stream, so
+	// that the FDCT kernel of one launch fills the SMs the pack kernel of the previous one leaves
+	// idle in its last wave, and the coefficient plane of a launch (reused every other launch)
+	// stays in L2 between the two kernels
+	cudaStream_t pipe[2] = {nullptr, nullptr};
+	cudaEvent_t pipe_fork = nullptr, pipe_join[2] = {nullptr, nullptr};
+	psxb200::DeviceBuffer<uint4> coefs2;
+	psxb200::DeviceBuffer<uint32_t> gstream2;
+	int device_pipeline = 1;            // PSXB200_DEVICE_PIPELINE=0 turns it off
 	BsSlot slots[BS_SLOTS];
 	BsLookahead ahead;
 	// optional per-kernel timing (psxb200_bs_timing_*): three events per internal launch pair

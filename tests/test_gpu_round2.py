@@ -70,6 +70,30 @@ def test_bs_large_budget_multi_chunk(restated):
     assert np.array_equal(got_out, exp_out)
 
 
+@pytest.mark.parametrize("n", [5, 200], ids=["few-frames-640-threads", "many-frames-320-threads"])
+@pytest.mark.parametrize("codec", [0, 1], ids=["v2", "v3"])
+def test_bs_busy_content_skips_hopeless_scales(restated, n, codec):
+    """Content far too busy for the small quant scales: the first pass overruns its budget early
+    and the census rules out the scales a lower bound proves hopeless. The result must still be
+    the reference's first-fit quant scale and bytes (mdec.c:663-722), for both CTA widths."""
+    w, h = 320, 240
+    rng = np.random.default_rng(n + codec)
+    frames = np.stack([synth.gen_frame(i, w, h, 6 if i % 3 else 5) for i in range(min(n, 10))])
+    frames = np.tile(frames, ((n + 9) // 10, 1))[:n].copy()
+    frames[:, ::11] ^= rng.integers(0, 8, size=(n, frames[:, ::11].shape[1]), dtype=np.uint8)
+    frames[-1] = rng.integers(0, 256, size=frames.shape[1], dtype=np.uint8)            # white noise: q ~ 40
+    sizes = np.array([(20160, 18144, 16128, 14112)[i % 4] for i in range(n)], np.int32)
+    enc = pb.BsEncoder(codec, w, h, pb.FDCT_SSE2, max_batch=256)
+    got_out, got_res = enc.encode_host(frames, sizes, stride=20160)
+    enc.close()
+    sel = np.arange(n) if n <= 16 else np.unique(np.concatenate([np.arange(0, n, 13), [n - 2, n - 1]]))
+    exp_out, exp_res = restated.bs_encode_batch(codec, w, h, frames[sel], sizes[sel], oracle.FDCT_SSE2, stride=20160)
+    assert exp_res[:, 2].min() >= 4 and exp_res[:, 2].max() < 64
+    assert np.array_equal(got_res[sel], exp_res)
+    for k, i in enumerate(sel):
+        assert np.array_equal(got_out[i, :sizes[i]], exp_out[k, :sizes[i]]), "frame %d" % i
+
+
 # ---- complete STR / STRCD sectors and file images ------------------------------------------------
 
 @pytest.mark.parametrize("fmt", [pb.FORMAT_STRCD, pb.FORMAT_STR], ids=["strcd", "str"])
