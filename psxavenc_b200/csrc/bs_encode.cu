@@ -619,7 +619,13 @@ __device__ __forceinline__ StrFrame str_frame(const BsStrLayout &str, int f) {
 	return sf;
 }
 
-template <bool V3, bool SMEM_STREAM, bool STR, int MAX_THREADS, int MIN_CTAS>
+// BUSY = false: the kernel every frame goes through. A frame whose first pass overruns its budget
+// before half of the frame has been priced is not finished here: its result row is marked
+// (quant_scale 0) and the CTA exits. BUSY = true: launched right behind it on the same stream,
+// takes only the marked frames, rules out the hopeless quant scales with the census and then
+// carries on with the first-fit search. (Two kernels rather than one branch: the extra code in the
+// common kernel cost it a third of its speed, measured.)
+template <bool V3, bool SMEM_STREAM, bool STR, bool BUSY, int MAX_THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS)
 bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk, int ngroups, int nsgroups, int cpad,
                int nmb, int codec,
@@ -629,6 +635,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
 	const int f = blockIdx.x;
+	if (BUSY && results[f].quant_scale != 0) return;   // finished by the first kernel
 	const int padded = nsgroups * 32;   // blocks in bitstream order, rounded up to whole scan groups
 	const int stream_words = (max_size_bound + 3) / 4 + 2;
 
@@ -695,9 +702,15 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	// pass whose running total passes it has failed (the reference's writer overflows at that
 	// point too, mdec.c:323-325) and is abandoned early.
 	const int limit_bits = max_size >= 8 ? 16 * ((max_size - 8) >> 1) - 10 : -1;
-	// the census needs CENSUS_BINS counters per thread in the (zeroed) shared-memory image
+	// the census needs CENSUS_BINS 16-bit counters per thread in the (zeroed) shared-memory image
 	const bool census_possible = SMEM_STREAM && 2 * words >= CENSUS_BINS * T;
 	int q = 1;
+	if (BUSY) {
+		// v2: 10-bit DC + 2-bit end of block per block; v3: DC codes are at least 2 bits long
+		q = census_first_candidate(fc, ngroups, cpad, nmb, s.grows, reinterpret_cast<uint16_t *>(s.stream), s.lenlut,
+		                           s.misc + 8, nblk * (V3 ? 4 : 12), limit_bits);
+		q = max(q, 2);   // q = 1 failed in the first kernel
+	}
 	uint32_t total_bits = 0;
 	for (; q < 64; q++) {
 		const QuantScale qs(q);
@@ -722,7 +735,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 			before = __shfl_sync(0xFFFFFFFFu, before, 0);
 			if ((int)(before + sum) > limit_bits) break;
 		}
-		if (q == 1 && lane == 0) atomicAdd(&s.misc[4], (uint32_t)visited);
+		if (!BUSY && q == 1 && lane == 0) atomicAdd(&s.misc[4], (uint32_t)visited);
 		__syncthreads();
 		total_bits = *total;
 		if (tid == 0) s.misc[(q + 2) % 3] = 0;
@@ -730,14 +743,10 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		int units = (int)((total_bits + 10 + 15) >> 4);
 		if (8 + 2 * units <= max_size) break;
 		// The first pass ran over its budget before it had seen half of the frame: the content is
-		// far too busy for the small quant scales. Rule the hopeless ones out in one go.
-		if (q == 1 && census_possible && 2 * (int)s.misc[4] < ngroups) {
-			// v2: 10-bit DC + 2-bit end of block per block; v3: DC codes are at least 2 bits long
-			const int first = census_first_candidate(fc, ngroups, cpad, nmb, s.grows, reinterpret_cast<uint16_t *>(s.stream), s.lenlut, s.misc + 8,
-			                                         nblk * (V3 ? 4 : 12), limit_bits);
-			if (tid < 3) s.misc[tid] = 0;
-			__syncthreads();
-			q = max(q, first - 1);   // the loop moves on to `first`
+		// far too busy for the small quant scales. Leave the frame to the BUSY kernel.
+		if (!BUSY && q == 1 && census_possible && 2 * (int)s.misc[4] < ngroups) {
+			if (tid == 0) results[f] = psxb200_bs_result_t{0, 0, 0, 0};
+			return;
 		}
 	}
 
@@ -944,12 +953,12 @@ cudaError_t bs_launch_dct(int fdct_variant, const uint8_t *d_frames, size_t fram
 	return cudaGetLastError();
 }
 
-template <bool V3, bool SMEM_STREAM, bool STR, int MAX_THREADS, int MIN_CTAS>
+template <bool V3, bool SMEM_STREAM, bool STR, bool BUSY, int MAX_THREADS, int MIN_CTAS>
 static cudaError_t launch_pack_t(int threads, size_t smem, int n, const uint4 *d_coefs, const BsGeometry &geo, int codec,
                                  const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
                                  psxb200_bs_result_t *d_results, uint32_t *d_gstream, size_t gstream_stride,
                                  const BsStrLayout &str, cudaStream_t stream) {
-	auto kern = bs_pack_kernel<V3, SMEM_STREAM, STR, MAX_THREADS, MIN_CTAS>;
+	auto kern = bs_pack_kernel<V3, SMEM_STREAM, STR, BUSY, MAX_THREADS, MIN_CTAS>;
 	// The opt-in to more than 48 KB of dynamic shared memory is a per-device attribute of this
 	// instantiation: raised to the hardware maximum once per device.
 	static bool configured[MAX_DEVICES];
@@ -974,7 +983,7 @@ static cudaError_t launch_pack_t(int threads, size_t smem, int n, const uint4 *d
 	return cudaGetLastError();
 }
 
-template <int MAX_THREADS, int MIN_CTAS>
+template <bool BUSY, int MAX_THREADS, int MIN_CTAS>
 static cudaError_t launch_pack_cfg(bool v3, bool smem_stream, int threads, size_t smem, int n, const uint4 *d_coefs,
                                    const BsGeometry &geo, int codec, const int *d_max_sizes, int max_size_bound,
                                    uint8_t *d_out, size_t out_stride, psxb200_bs_result_t *d_results,
@@ -982,18 +991,18 @@ static cudaError_t launch_pack_cfg(bool v3, bool smem_stream, int threads, size_
                                    cudaStream_t stream) {
 #define PSXB200_PACK_ARGS threads, smem, n, d_coefs, geo, codec, d_max_sizes, max_size_bound, d_out, out_stride, \
 	d_results, d_gstream, gstream_stride, str, stream
-	if (str.sector_size) {
-		if (v3)
-			return smem_stream ? launch_pack_t<true, true, true, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
-			                   : launch_pack_t<true, false, true, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
-		return smem_stream ? launch_pack_t<false, true, true, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
-		                   : launch_pack_t<false, false, true, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
+	if (BUSY || smem_stream) {   // the BUSY kernel exists for the shared-memory image only (its census lives there)
+		if (str.sector_size)
+			return v3 ? launch_pack_t<true, true, true, BUSY, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
+			          : launch_pack_t<false, true, true, BUSY, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
+		return v3 ? launch_pack_t<true, true, false, BUSY, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
+		          : launch_pack_t<false, true, false, BUSY, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
 	}
-	if (v3)
-		return smem_stream ? launch_pack_t<true, true, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
-		                   : launch_pack_t<true, false, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
-	return smem_stream ? launch_pack_t<false, true, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
-	                   : launch_pack_t<false, false, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
+	if (str.sector_size)
+		return v3 ? launch_pack_t<true, false, true, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
+		          : launch_pack_t<false, false, true, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
+	return v3 ? launch_pack_t<true, false, false, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
+	          : launch_pack_t<false, false, false, false, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);
 #undef PSXB200_PACK_ARGS
 }
 
@@ -1006,15 +1015,19 @@ cudaError_t bs_launch_pack(int codec, int threads, int min_ctas, int n, const ui
 	size_t smem = bs_pack_smem_bytes(v3, smem_stream, geo, max_size_bound, threads);
 #define PSXB200_CFG_ARGS v3, smem_stream, threads, smem, n, d_coefs, geo, codec, d_max_sizes, max_size_bound, d_out, \
 	out_stride, d_results, d_gstream, gstream_stride, str, stream
-	// register budget variants: (max threads per CTA, CTAs per SM the register file must hold)
+	// register budget variants: (max threads per CTA, CTAs per SM the register file must hold).
+	// The common kernel first, then — shared-memory image only — the kernel for the frames it deferred.
+	cudaError_t e;
 	if (threads <= 320) {
-		if (min_ctas >= 4) return launch_pack_cfg<320, 4>(PSXB200_CFG_ARGS);
-		if (min_ctas == 3) return launch_pack_cfg<320, 3>(PSXB200_CFG_ARGS);
-		return launch_pack_cfg<320, 2>(PSXB200_CFG_ARGS);
+		if (min_ctas >= 4) {
+			e = launch_pack_cfg<false, 320, 4>(PSXB200_CFG_ARGS);
+			return e != cudaSuccess || !smem_stream ? e : launch_pack_cfg<true, 320, 4>(PSXB200_CFG_ARGS);
+		}
+		e = launch_pack_cfg<false, 320, 3>(PSXB200_CFG_ARGS);
+		return e != cudaSuccess || !smem_stream ? e : launch_pack_cfg<true, 320, 3>(PSXB200_CFG_ARGS);
 	}
-	if (threads <= 448 && min_ctas >= 3) return launch_pack_cfg<448, 3>(PSXB200_CFG_ARGS);
-	if (min_ctas >= 2) return launch_pack_cfg<BS_PACK_MAX_THREADS, 2>(PSXB200_CFG_ARGS);
-	return launch_pack_cfg<BS_PACK_MAX_THREADS, 1>(PSXB200_CFG_ARGS);
+	e = launch_pack_cfg<false, BS_PACK_MAX_THREADS, 1>(PSXB200_CFG_ARGS);
+	return e != cudaSuccess || !smem_stream ? e : launch_pack_cfg<true, BS_PACK_MAX_THREADS, 1>(PSXB200_CFG_ARGS);
 #undef PSXB200_CFG_ARGS
 }
 

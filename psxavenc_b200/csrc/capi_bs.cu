@@ -218,7 +218,7 @@ static int bs_encode_chunked(psxb200_bs_encoder *enc, DeviceBuffer<uint4> &coefs
 		                      str_batch ? d_out : d_out + (size_t)first * out_stride, out_stride, d_results + first, gstream,
 		                      gstride, str, stream));
 		if (enc->timing) CU_TRY(enc->mark(stream));
-		g_launches += 2;
+		g_launches += gstream ? 2 : 3;   // FDCT, pack, and (shared-memory image) the pack kernel for deferred frames
 		if (str_batch && str.framing && str.format != FORMAT_STRV) {
 			CU_TRY(bs_launch_str_framing(m, max_size_bound / 2016, d_out, str, stream));
 			g_launches += 1;
