@@ -825,18 +825,24 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		uint32_t *stage = s.stage + tid;
 		uint32_t nnz = 0;
 		for (int g = ngroups - 1 - wid; g >= 0; g -= nw) {
+			// Lanes walk different numbers of coefficients, so the warp is brought back together
+			// (__syncwarp) before every convergent stretch — left to itself it ran the staging code
+			// below in up to seven separate lane groups per group of blocks (ncu: executed 395
+			// instead of 57 times per frame). Padding lanes (b < 0) come along with empty lists.
 			const int b = bs_plane_to_block(g * 32 + lane, cpad, nmb);
-			if (b < 0) continue;
+			const bool act = b >= 0;
 			const uint4 *gp = fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane;
 			const uint4 meta = gp[BS_META_ROW * 32];
 			const int nrows = s.grows[g];
 			BitWriter bw;
-			bw.begin(stream, s.gtot[b >> 5] + s.lens[b]);
-			if (V3) {
-				uint32_t e = dc_code(b);
-				bw.put((int)(e >> 24), e & 0xFFFFFFu);
-			} else {
-				bw.put(10, (uint32_t)quant_dc(meta.z & 0xFFFFu, meta.x & 1u) & 0x3FFu);
+			bw.begin(stream, act ? s.gtot[b >> 5] + s.lens[b] : 0u);
+			if (act) {
+				if (V3) {
+					uint32_t e = dc_code(b);
+					bw.put((int)(e >> 24), e & 0xFFFFFFu);
+				} else {
+					bw.put(10, (uint32_t)quant_dc(meta.z & 0xFFFFu, meta.x & 1u) & 0x3FFu);
+				}
 			}
 			int prev = 0;
 			// one coefficient: y at zig-zag position pos (mdec.c:484-499)
@@ -856,7 +862,9 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 			};
 			if (nrows & 0x80) {
 				for (int half = 0; half < 2; half++) {
+					__syncwarp();
 					uint32_t live = stage_dense(gp, half, qs, stage, T);
+					if (!act) live = 0;
 					nnz += __popc(live);
 					while (live) {
 						const int e = __ffs((int)live) - 1;
@@ -867,7 +875,9 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 				}
 			} else {
 				for (int r0 = nrows > 4 ? 4 : 0; r0 >= 0; r0 -= 4) {
+					__syncwarp();
 					uint32_t live = stage_rows(gp, r0, min(nrows - r0, 4), qs, stage, T);
+					if (!act) live = 0;
 					nnz += __popc(live);
 					while (live) {
 						const int e = 32 - __ffs((int)live);   // local entry, highest (= lowest position) first
@@ -878,10 +888,14 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 					}
 				}
 			}
-			bw.put(2, 2u);   // end of block (mdec.c:502)
-			if (b == nblk - 1) bw.put(10, V3 ? 0x3FFu : 0x1FFu);   // end of frame (mdec.c:645-652, 710)
-			bw.finish();
+			__syncwarp();
+			if (act) {
+				bw.put(2, 2u);   // end of block (mdec.c:502)
+				if (b == nblk - 1) bw.put(10, V3 ? 0x3FFu : 0x1FFu);   // end of frame (mdec.c:645-652, 710)
+				bw.finish();
+			}
 		}
+		__syncwarp();
 		nnz = warp_sum(nnz);
 		if (lane == 0) atomicAdd(&s.misc[3], nnz);
 	}

@@ -157,6 +157,8 @@ extern "C" void psxb200_bs_destroy(psxb200_bs_encoder_t *enc) {
 		cudaStreamSynchronize(a.stream);
 		cudaStreamDestroy(a.stream);
 	}
+	for (auto &g : a.graphs)
+		if (g.exec) cudaGraphExecDestroy(g.exec);
 	a.staged.release();
 	a.h_out.release();
 	a.h_res.release();
@@ -888,25 +890,77 @@ extern "C" void encode_frame_bs(mdec_encoder_t *encoder, const uint8_t *video_fr
 // frame it is handed with the staged copy (all bytes) and its budget with the predicted one; on
 // a match the finished result is taken, otherwise the speculation is dropped and the frame is
 // encoded synchronously. Output bytes are the same either way.
-static int lookahead_start(psxb200_bs_encoder *enc, const uint8_t *frame, int max_size) {
+static int lookahead_enqueue(psxb200_bs_encoder *enc, int max_size) {
 	BsLookahead &a = enc->ahead;
-	a.valid = false;
-	if (max_size < 8) return 0;
-	if (!a.stream) CU_TRY(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
-	CU_TRY(a.staged.reserve(enc->frame_bytes));
-	CU_TRY(a.h_out.reserve((size_t)max_size));
-	CU_TRY(a.h_res.reserve(1));
-	CU_TRY(a.in.reserve(enc->frame_bytes));
-	CU_TRY(a.out.reserve(round_up((size_t)max_size, 16)));
-	CU_TRY(a.res.reserve(1));
-	memcpy(a.staged.ptr, frame, enc->frame_bytes);
 	CU_TRY(cudaMemcpyAsync(a.in.ptr, a.staged.ptr, enc->frame_bytes, cudaMemcpyHostToDevice, a.stream));
 	if (bs_encode_chunked(enc, a.coefs, a.gstream, 1, a.in.ptr, nullptr, max_size, a.out.ptr, round_up((size_t)max_size, 16),
 	                      a.res.ptr, a.stream))
 		return -1;
 	CU_TRY(cudaMemcpyAsync(a.h_out.ptr, a.out.ptr, (size_t)max_size, cudaMemcpyDeviceToHost, a.stream));
 	CU_TRY(cudaMemcpyAsync(a.h_res.ptr, a.res.ptr, sizeof(psxb200_bs_result_t), cudaMemcpyDeviceToHost, a.stream));
+	return 0;
+}
+
+static int lookahead_start(psxb200_bs_encoder *enc, const uint8_t *frame, int max_size) {
+	BsLookahead &a = enc->ahead;
+	a.valid = false;
+	if (max_size < 8) return 0;
+	if (!a.stream) CU_TRY(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+	// buffers are sized for the largest budget seen so far; growing one invalidates the graphs
+	// (they hold the old addresses)
+	const size_t want_out = round_up((size_t)max_size, 16);
+	if (a.h_out.cap < (size_t)max_size || a.out.cap < want_out || !a.staged.ptr) {
+		for (auto &g : a.graphs) {
+			if (g.exec) cudaGraphExecDestroy(g.exec);
+			g = BsLookahead::Graph();
+		}
+		CU_TRY(cudaStreamSynchronize(a.stream));
+		CU_TRY(a.staged.reserve(enc->frame_bytes));
+		CU_TRY(a.h_out.reserve((size_t)max_size));
+		CU_TRY(a.h_res.reserve(1));
+		CU_TRY(a.in.reserve(enc->frame_bytes));
+		CU_TRY(a.out.reserve(want_out));
+		CU_TRY(a.res.reserve(1));
+	}
+	memcpy(a.staged.ptr, frame, enc->frame_bytes);
 	a.max_size = max_size;
+
+	BsLookahead::Graph *slot = nullptr;
+	for (auto &g : a.graphs)
+		if (g.max_size == max_size) slot = &g;
+	if (!slot)
+		for (auto &g : a.graphs)
+			if (!slot && g.max_size == 0) slot = &g;
+	if (slot && !enc->timing) {
+		slot->max_size = max_size;
+		if (!slot->exec && slot->uses++ > 0) {
+			// second speculation with this budget (the first one ran eagerly and sized every
+			// scratch buffer): record the sequence once
+			cudaGraph_t graph = nullptr;
+			CU_TRY(cudaStreamBeginCapture(a.stream, cudaStreamCaptureModeThreadLocal));
+			const int rc = lookahead_enqueue(enc, max_size);
+			cudaError_t e = cudaStreamEndCapture(a.stream, &graph);
+			if (rc || e != cudaSuccess) {
+				if (graph) cudaGraphDestroy(graph);
+				cudaGetLastError();
+				slot->uses = -1000000;   // do not try again; run eagerly
+			} else {
+				e = cudaGraphInstantiate(&slot->exec, graph, 0);
+				cudaGraphDestroy(graph);
+				if (e != cudaSuccess) {
+					slot->exec = nullptr;
+					slot->uses = -1000000;
+					cudaGetLastError();
+				}
+			}
+		}
+		if (slot->exec) {
+			CU_TRY(cudaGraphLaunch(slot->exec, a.stream));
+			a.valid = true;
+			return 0;
+		}
+	}
+	if (lookahead_enqueue(enc, max_size)) return -1;
 	a.valid = true;
 	return 0;
 }

@@ -44,6 +44,13 @@ struct BsLookahead {
 	psxb200::DeviceBuffer<psxb200_bs_result_t> res;
 	psxb200::DeviceBuffer<uint4> coefs;
 	psxb200::DeviceBuffer<uint32_t> gstream;
+	// the copy-in / kernels / copy-out sequence of one speculation as an instantiated CUDA graph
+	// per byte budget (all its pointers are the fixed staging buffers above): one launch call
+	// instead of six, and no gaps between the dependent operations on the device
+	struct Graph {
+		int max_size = 0, uses = 0;
+		cudaGraphExec_t exec = nullptr;
+	} graphs[4];
 };
 
 struct psxb200_bs_encoder {

@@ -84,6 +84,24 @@ def test_driver_spui_loop(driver, restated, tmp_path):
     assert np.array_equal(got, np.concatenate(chunks))
 
 
+@pytest.mark.gpu
+def test_driver_multi_device_entry(driver, restated, tmp_path):
+    """A plain C host (compiled against the reference's headers plus the additive psxb200_* layer)
+    driving two devices from one process through psxb200_bs_multi_encode_host with pinned buffers
+    from psxb200_pinned_alloc; output and result rows byte-equal to the oracle."""
+    w, h, n, size = 320, 240, 41, 18144
+    frames = synth.gen_frames(5, n, w, h, 3)
+    frames.tofile(tmp_path / "in.nv21")
+    subprocess.run([driver, "multi", str(w), str(h), "1", str(size), str(n), "2", str(tmp_path / "in.nv21"), str(tmp_path / "out.bin")],
+                   check=True, timeout=120)
+    raw = np.fromfile(tmp_path / "out.bin", dtype=np.uint8)
+    got = raw[:n * size].reshape(n, size)
+    res = raw[n * size:].view(np.int32).reshape(n, 4)
+    exp, exp_res = restated.bs_encode_batch(1, w, h, frames, size, oracle.FDCT_ISLOW)
+    assert np.array_equal(res, exp_res)
+    assert np.array_equal(got, exp)
+
+
 def _mux_strcd(lib, frames, pcm, n_sectors, w, h):
     """The sector schedule of encode_file_str (filefmt.c:391-520) for -t strcd defaults: 2x speed,
     15 fps, 37800 Hz 4-bit stereo XA -> interleave 8 (1 audio + 7 video sectors), driven through

@@ -100,3 +100,15 @@ for k in range(200):
     lib.psx_audio_xa_encode(xa, C.addressof(state), stereo.ctypes.data + 4 * 2016 * k, 2016, k, sector.ctypes.data)
 dt = time.perf_counter() - t0
 print("psx_audio_xa_encode drop-in (one 2352-byte sector per call): %.1f us/call, %.2f Msamples/s" % (dt / 200 * 1e6, 200 * 4032 / dt / 1e6))
+
+# the same sector loop from plain C (no Python between the calls), with and without caller-side work
+import subprocess, tempfile
+import oracle
+oracle.build()
+if os.path.exists(oracle.DROPIN_DRIVER):
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "in.nv21")
+        frames.tofile(path)
+        for work in ("0", "150"):
+            print(subprocess.run([oracle.DROPIN_DRIVER, "strvbench", str(w), str(h), "1500", work, path], capture_output=True,
+                                 text=True, timeout=300).stdout.strip())
