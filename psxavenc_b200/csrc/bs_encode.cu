@@ -545,26 +545,39 @@ __device__ __forceinline__ int quant_dc(uint32_t mag, uint32_t negative) {
 // that is nonzero at q costs at least the run-0 code of its level (the shortest code of a level,
 // and lengths grow with the level), so  fixed + sum over entries of len(level(y, q), run 0)  is a
 // lower bound of the frame's bit total at q; capping y at 15 only lowers it further. One walk over
-// the lists builds a histogram of min(y, 15) — per-thread 16-bit counters in the (still zero)
-// bitstream image, so no two threads ever touch the same counter (a thread sees at most
-// 64 * ceil(groups / warps) <= 1536 entries) — from which the bound follows for all q at once. Called by all threads of the CTA; returns the smallest q >= 2 the bound cannot exclude
-// (64: none) and leaves `bins` zeroed again.
+// the lists builds a histogram of min(y, 15): each thread adds, per entry, a 128-bit word from a
+// 16-entry table that holds a one in the byte of the entry's bin (a block has at most 64 entries,
+// so the byte counters cannot overflow within a block), and unpacks the bytes into its 15
+// counters once per block. From the CTA-wide sums the bound follows for all q at once.
+// Called by all threads of the CTA; returns the smallest q >= 2 the bound cannot exclude (64: none).
 constexpr int CENSUS_BINS = 15;
 
 __device__ __noinline__ int census_first_candidate(const uint4 *__restrict__ fc, int ngroups, int cpad, int nmb,
-                                                   const uint8_t *grows, uint16_t *bins, const uint8_t *lenlut,
-                                                   uint32_t *scratch /* >= 64 words */, int fixed_bits, int limit_bits) {
+                                                   const uint8_t *grows, const uint8_t *lenlut,
+                                                   uint32_t *scratch /* >= 128 words */, int fixed_bits, int limit_bits) {
 	const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
-	uint16_t *mine = bins + tid;
-	auto count = [&](uint32_t y) {
-		if (y) mine[(min(y, (uint32_t)CENSUS_BINS) - 1) * T]++;
-	};
+	uint4 *onehot = reinterpret_cast<uint4 *>(scratch + 64);   // [min(y, 15)] -> a one in byte (bin - 1), zero for y = 0
+	if (tid < 16) {
+		uint32_t w[4] = {0, 0, 0, 0};
+		if (tid) w[(tid - 1) >> 2] = 1u << (8 * ((tid - 1) & 3));
+		onehot[tid] = make_uint4(w[0], w[1], w[2], w[3]);
+	}
+	if (tid < 64) scratch[tid] = tid == CENSUS_BINS ? 64u : 0u;   // [0..14] bin totals, [15] the answer
+	__syncthreads();
+	uint32_t bins[CENSUS_BINS];
+#pragma unroll
+	for (int b = 0; b < CENSUS_BINS; b++) bins[b] = 0;
 	for (int g = ngroups - 1 - wid; g >= 0; g -= nw) {
 		if (bs_plane_to_block(g * 32 + lane, cpad, nmb) < 0) continue;
 		const uint4 *gp = fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane;
 		const int rows = grows[g];
 		const bool dense = rows & 0x80;
 		const int nrows = dense ? 8 : rows;
+		uint4 acc = make_uint4(0, 0, 0, 0);
+		auto count = [&](uint32_t y) {
+			const uint4 one = onehot[min(y, (uint32_t)CENSUS_BINS)];
+			acc.x += one.x; acc.y += one.y; acc.z += one.z; acc.w += one.w;
+		};
 		for (int r = 0; r < nrows; r++) {
 			const uint4 w = gp[r * 32];
 			const uint32_t v[4] = {w.x, w.y, w.z, w.w};
@@ -575,18 +588,14 @@ __device__ __noinline__ int census_first_candidate(const uint4 *__restrict__ fc,
 				count(dense ? v[t] >> 16 : v[t] >> 22);
 			}
 		}
+		const uint32_t a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+		for (int b = 0; b < CENSUS_BINS; b++) bins[b] += (a[b >> 2] >> (8 * (b & 3))) & 0xFFu;
 	}
-	__syncthreads();
-	if (tid < 64) scratch[tid] = tid == CENSUS_BINS ? 64u : 0u;   // [0..14] bin totals, [15] the answer
-	__syncthreads();
-	for (int b = wid; b < CENSUS_BINS; b += nw) {
-		uint32_t sum = 0;
-		for (int i = lane; i < T; i += 32) {
-			sum += bins[b * T + i];
-			bins[b * T + i] = 0;
-		}
-		sum = warp_sum(sum);
-		if (lane == 0) scratch[b] = sum;
+#pragma unroll
+	for (int b = 0; b < CENSUS_BINS; b++) {
+		const uint32_t sum = warp_sum(bins[b]);
+		if (lane == 0 && sum) atomicAdd(&scratch[b], sum);
 	}
 	__syncthreads();
 	if (tid >= 2 && tid < 64) {
@@ -702,13 +711,12 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	// pass whose running total passes it has failed (the reference's writer overflows at that
 	// point too, mdec.c:323-325) and is abandoned early.
 	const int limit_bits = max_size >= 8 ? 16 * ((max_size - 8) >> 1) - 10 : -1;
-	// the census needs CENSUS_BINS 16-bit counters per thread in the (zeroed) shared-memory image
-	const bool census_possible = SMEM_STREAM && 2 * words >= CENSUS_BINS * T;
+	// frames with a tiny budget are not worth a second kernel
+	const bool census_possible = SMEM_STREAM && max_size >= 2016;
 	int q = 1;
 	if (BUSY) {
 		// v2: 10-bit DC + 2-bit end of block per block; v3: DC codes are at least 2 bits long
-		q = census_first_candidate(fc, ngroups, cpad, nmb, s.grows, reinterpret_cast<uint16_t *>(s.stream), s.lenlut,
-		                           s.misc + 8, nblk * (V3 ? 4 : 12), limit_bits);
+		q = census_first_candidate(fc, ngroups, cpad, nmb, s.grows, s.lenlut, s.misc + 8, nblk * (V3 ? 4 : 12), limit_bits);
 		q = max(q, 2);   // q = 1 failed in the first kernel
 	}
 	uint32_t total_bits = 0;
@@ -1005,7 +1013,7 @@ static cudaError_t launch_pack_cfg(bool v3, bool smem_stream, int threads, size_
                                    cudaStream_t stream) {
 #define PSXB200_PACK_ARGS threads, smem, n, d_coefs, geo, codec, d_max_sizes, max_size_bound, d_out, out_stride, \
 	d_results, d_gstream, gstream_stride, str, stream
-	if (BUSY || smem_stream) {   // the BUSY kernel exists for the shared-memory image only (its census lives there)
+	if (BUSY || smem_stream) {   // the BUSY kernel is instantiated for the shared-memory image only
 		if (str.sector_size)
 			return v3 ? launch_pack_t<true, true, true, BUSY, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS)
 			          : launch_pack_t<false, true, true, BUSY, MAX_THREADS, MIN_CTAS>(PSXB200_PACK_ARGS);

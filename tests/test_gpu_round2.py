@@ -320,6 +320,31 @@ def test_bs_multi_device_host_entry(restated):
     multi.close()
 
 
+def test_strcd_images_over_devices(reference):
+    """psxb200_bs_multi_strcd_encode_host: whole files dealt out over the devices."""
+    w, h, fpf, n_files, interleave = 320, 240, 4, 5, 8
+    frames = synth.gen_frames(7, fpf * n_files, w, h, 3)
+    params = pb.str_params(pb.FORMAT_STRCD, 150 * 7, 15 * 8, interleave=interleave, xa_file=1, xa_channel=0)
+    probe, _ = reference.str_mux(0, w, h, frames[:fpf], fmt=pb.FORMAT_STRCD, pcm=np.zeros(2 * 2016 * 40, np.int16), n_samples=2016 * 40)
+    n_sectors = probe.shape[0]
+    samples = ((n_sectors + interleave - 1) // interleave) * 2016
+    pcm = np.stack([np.concatenate([synth.gen_pcm(samples, 2, 90 + f).ravel(), np.zeros(256, np.int16)]) for f in range(n_files)])
+    size = int(pb.lib().psxb200_strcd_image_bytes(C.byref(params), fpf, 4, 1, samples))
+    assert size == n_sectors * 2352
+    images = np.zeros((n_files, size), np.uint8)
+    res = np.zeros((fpf * n_files, 4), np.int32)
+    multi = pb.BsMultiEncoder(0, w, h, pb.FDCT_ISLOW, max_batch=4, device_ids=_device_ids(2))
+    rc = pb.lib().psxb200_bs_multi_strcd_encode_host(multi.handle, n_files, fpf, frames.ctypes.data, C.byref(params), 37800, 4, 1,
+                                                     pcm.ctypes.data, pcm.shape[1], samples, None, images.ctypes.data, size,
+                                                     res.ctypes.data)
+    assert rc == 0, pb.last_error()
+    for f in range(n_files):
+        exp, qsum = reference.str_mux(0, w, h, frames[f * fpf:(f + 1) * fpf], fmt=pb.FORMAT_STRCD, pcm=pcm[f], n_samples=samples)
+        assert np.array_equal(images[f], exp.ravel()), "file %d" % f
+        assert res[f * fpf:(f + 1) * fpf, 2].sum() == qsum
+    multi.close()
+
+
 def test_spu_multi_device_channel_split(restated):
     """`vagi`: one 8-channel file, chain c on device c mod G; and `vagi x B`: whole files per device."""
     ch, count = 8, 3584 + 280

@@ -55,3 +55,41 @@ def test_budget_rule_matches_byte_writer():
     for max_size in (8, 9, 10, 11, 12, 64, 65, 2016, 2017):
         for bits in range(1, 16 * 40):
             assert writer_fits(bits, max_size) == (8 + 2 * ((bits + 15) // 16) <= max_size), (bits, max_size)
+
+
+def test_list_entry_fields_cannot_overflow(restated):
+    """A list entry packs y = floor(2|c| / quant) into 10 bits beside the 6-bit position
+    (bs_encode.cu: (y << 6) | i): y must stay below 1024 for any 8-bit input. The coefficient of
+    a basis function is largest for its own 0/255 sign pattern, so those 128 blocks (and their
+    row/column-only variants) bound |c| for both FDCT variants; also the census' run-0 code
+    lengths must be the shortest of each level and grow with the level."""
+    import re
+    n = np.arange(8)
+    blocks = []
+    for u in range(8):
+        for v in range(8):
+            basis = np.outer(np.cos((2 * n + 1) * u * np.pi / 16), np.cos((2 * n + 1) * v * np.pi / 16))
+            for pat in (basis > 0, basis < 0, basis >= 0):
+                blocks.append(np.where(pat, 127, -128))
+    rng = np.random.default_rng(0)
+    blocks += [rng.choice([-128, 127], size=(8, 8)) for _ in range(2000)]
+    blocks = np.stack(blocks).astype(np.int16).reshape(-1, 64)
+    zigzag = [0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+              35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63]
+    quant_zz = np.array([QUANT[r] for r in zigzag], dtype=np.int64)
+    for variant in (0, 1):
+        co = np.abs(restated.fdct(variant, blocks).astype(np.int64))[:, zigzag]
+        y = (2 * co[:, 1:]) // quant_zz[None, 1:]
+        assert co[:, 1:].max() < 8192 and y.max() < 1024, (variant, int(co[:, 1:].max()), int(y.max()))
+    # VLC lengths: the table the kernels use (generated from the MPEG-1 code strings)
+    import os
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "psxavenc_b200", "csrc", "bs_tables.h")).read()
+    m = re.search(r"BS_AC_VLC\[[^\]]*\]\s*=\s*\{(.*?)\};", text, re.S)
+    vlc = np.array([int(x, 0) for x in re.findall(r"0x[0-9a-fA-F]+|\d+", m.group(1))]).reshape(32, 41)
+    lens = np.full((64, 64), 22)
+    for lv in range(1, 41):
+        for run in range(32):
+            if vlc[run, lv]:
+                lens[lv, run] = vlc[run, lv] >> 24
+    assert all(lens[lv].min() == lens[lv, 0] for lv in range(1, 64))
+    assert all(lens[lv, 0] <= lens[lv + 1, 0] for lv in range(1, 63))
