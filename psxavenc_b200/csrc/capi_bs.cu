@@ -331,6 +331,8 @@ extern "C" int psxb200_bs_encode_host(psxb200_bs_encoder_t *enc, int n, const ui
 	// rest of every budget (the reference clears the whole buffer, mdec.c:676). Phase B of a
 	// chunk is issued after phase A of the next one, so the copy engines stay busy.
 	const int hc = enc->host_chunk;
+	// experiments only (tools/e2e_probe.py): leave the zero fill of the tails out to see what it costs
+	static const bool skip_tail_zero = getenv("PSXB200_EXPERIMENT_SKIP_TAIL_ZERO") != nullptr;
 	BsChunk inflight[BS_SLOTS];
 	bool busy[BS_SLOTS] = {};
 
@@ -391,7 +393,7 @@ extern "C" int psxb200_bs_encode_host(psxb200_bs_encoder_t *enc, int n, const ui
 				CU_TRY(cudaMemcpyAsync(row + width, s.out.ptr + (size_t)i * c.dstride + width, (size_t)(used - width),
 				                       cudaMemcpyDeviceToHost, s.stream));
 			const int clean_from = std::max(used, width);
-			if (budget > clean_from) memset(row + clean_from, 0, (size_t)(budget - clean_from));
+			if (budget > clean_from && !skip_tail_zero) memset(row + clean_from, 0, (size_t)(budget - clean_from));
 			h_results[c.first + i] = s.h_res.ptr[i];
 		}
 		return 0;
