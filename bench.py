@@ -896,6 +896,31 @@ def bench_vagi(ctx, files):
     out["e2e"] = {"value": ctx.world * streams * count * reps / dt / 1e6, "unit": "Msamples/s",
                   "h2d_bytes_per_step": streams * count * 2 + streams * 24, "d2h_bytes_per_step": streams * row + streams * 24,
                   "api": "psxb200_spu_encode_host (pinned host buffers)"}
+    # the same file(s) of rank 0 dealt over ALL GPUs by one process: whole files per device when
+    # there are enough of them, else channel c on device c mod G — a single stream
+    # gains nothing from more devices, its channels are serial chains that already run side by side
+    if ctx.world > 1 and pb.device_count() >= ctx.world:
+        ctx.host_barrier()
+        if ctx.rank == 0:
+            m_out = torch.empty((streams, row), dtype=torch.uint8, pin_memory=True)
+
+            def multi_call():
+                h_states.zero_()
+                rc = lib.psxb200_spu_encode_host_multi(ctx.world, None, streams, h_pcm.data_ptr(), ch, count * ch, count,
+                                                       h_states.data_ptr(), m_out.data_ptr(), row)
+                assert rc == 0, pb.last_error()
+
+            multi_call()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                multi_call()
+            mdt = time.perf_counter() - t0
+            if not np.array_equal(m_out.numpy(), got_all):
+                raise SystemExit("bench.py: SPU-ADPCM output of the multi-device entry differs")
+            out["over_devices"] = {"value": streams * count * reps / mdt / 1e6, "unit": "Msamples/s", "devices": ctx.world,
+                                   "split": "whole files per device" if files >= ctx.world else "channel c on device c mod G",
+                                   "api": "psxb200_spu_encode_host_multi (one process, rank 0's streams only)"}
+        ctx.host_barrier()
     return out
 
 

@@ -144,9 +144,14 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
               int mbh, uint32_t mbh_magic, int nmb, int cpad, int ngroups, uint4 *__restrict__ coefs,
               size_t frame_stride_u4) {
 	// Per-thread list columns: entry k of thread t at s_list[k * BS_DCT_THREADS + t] (a warp's
-	// appends fall into distinct banks whatever the lanes' fill levels). Never initialised: a
-	// column is only read back below its own fill level (no block-wide zeroing, no barrier).
+	// appends fall into distinct banks whatever the lanes' fill levels). Zeroed first so that the
+	// tail of every list reads as "no coefficient" (masking the tail on read-back instead, without
+	// this block-wide zeroing and its barrier, measured 3 % slower).
 	__shared__ __align__(16) uint16_t s_list[64 * BS_DCT_THREADS];
+#pragma unroll
+	for (int j = 0; j < (64 * 2) / 16; j++)
+		reinterpret_cast<uint4 *>(s_list)[threadIdx.x + BS_DCT_THREADS * j] = make_uint4(0, 0, 0, 0);
+	__syncthreads();
 
 	// grid: x = chunk of 128 plane lanes within the frame, y = frame
 	const int f = blockIdx.y;
@@ -255,14 +260,10 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
 		const int nrows = (longest + 7) >> 3;
 		for (int r = 0; r < nrows; r++) {
 			const uint16_t *e = col + 8 * r * BS_DCT_THREADS;
-			const int left = count - 8 * r;   // entries of this list in rows r.. (may be <= 0)
 			uint32_t w[4];
 #pragma unroll
-			for (int t = 0; t < 4; t++) {
-				const uint32_t lo = 2 * t < left ? e[(2 * t) * BS_DCT_THREADS] : 0u;
-				const uint32_t hi = 2 * t + 1 < left ? e[(2 * t + 1) * BS_DCT_THREADS] : 0u;
-				w[t] = lo | (hi << 16);
-			}
+			for (int t = 0; t < 4; t++)
+				w[t] = (uint32_t)e[(2 * t) * BS_DCT_THREADS] | ((uint32_t)e[(2 * t + 1) * BS_DCT_THREADS] << 16);
 			dst[r * 32] = make_uint4(w[0], w[1], w[2], w[3]);
 		}
 	}

@@ -86,3 +86,26 @@ def test_xa_random(restated, reference, stereo, bits, fmt):
         b = reference.xa_encode(fmt, stereo, 18900 if bits == 8 else 37800, bits, 3, 5, s2, pcm, count, 1234, finalize=True)
         assert np.array_equal(a, b)
         assert bytes(s1) == bytes(s2)
+
+
+@pytest.mark.parametrize("codec", [0, 1, 2], ids=["v2", "v3", "v3dc"])
+@pytest.mark.parametrize("fdct", [oracle.FDCT_ISLOW, oracle.FDCT_SSE2], ids=["islow", "sse2"])
+def test_bs_baseline_shapes(restated, reference, codec, fdct):
+    """The port against the unmodified reference at the BASELINE shapes themselves: 320x240 with
+    the strv and strcd budgets over easy / typical / hard content, and 640x480 with the sbs
+    budget — so that GPU tests which compare with the port inherit the reference's bytes."""
+    w, h = 320, 240
+    frames = np.stack([synth.gen_frame(i, w, h, noise_bits=(0, 3, 5, 6)[i % 4]) for i in range(8)])
+    sizes = np.array([20160, 18144, 16128, 20160, 18144, 16128, 20160, 18144], np.int32)
+    o1, r1 = restated.bs_encode_batch(codec, w, h, frames, sizes, fdct, stride=20160)
+    o2, r2 = reference.bs_encode_batch(codec, w, h, frames, sizes, fdct, stride=20160)
+    assert np.array_equal(r1, r2) and len(set(r1[:, 2])) >= 3
+    for i, s in enumerate(sizes):     # the reference stores one stray byte AT frame_max_size when a pass overflows
+        assert np.array_equal(o1[i, :s], o2[i, :s]), "frame %d" % i
+    if codec:
+        w, h = 640, 480
+        frames = np.stack([synth.gen_smooth_frame(i, w, h, amplitude=20 + 9 * i, fx=0.006 + 0.002 * i, fy=0.009 + 0.001 * i)
+                           for i in range(3)])
+        o1, r1 = restated.bs_encode_batch(codec, w, h, frames, 8192, fdct)
+        o2, r2 = reference.bs_encode_batch(codec, w, h, frames, 8192, fdct)
+        assert np.array_equal(r1, r2) and np.array_equal(o1, o2)
