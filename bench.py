@@ -73,6 +73,14 @@ class Workload:
         return np.tile(base, (reps, 1))[:count]
 
 
+def headline_config(fdct_name):
+    """`config` of the JSON line — the same dict in both arms, so that the driver can tell they ran
+    the same thing; what only concerns one arm is in `config_detail`."""
+    return {"workload": WORKLOAD, "fdct": fdct_name,
+            "l2": "GPU arm: inputs larger than L2 (%.0f MB of frames per step per GPU, every frame distinct); "
+                  "reference arm: the same frames in host memory" % (FRAMES_PER_STEP * 115200 / 1e6)}
+
+
 STRV = Workload("strv", 320, 240, 0, 20160, FRAMES_PER_STEP, noise=3)
 WORKLOAD = "strv: 320x240 BS v2, frame_max_size 20160 B, %d synthetic NV21 frames per step per GPU, noise_bits=3 (quant scale 2)" % FRAMES_PER_STEP
 
@@ -169,7 +177,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "fdct": args.fdct, "sample": sample},
+        "config": headline_config(args.fdct), "config_detail": {"sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -501,12 +509,12 @@ def bench_headline(ctx, line):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "fdct": args.fdct, "frames_per_launch": frames_per_launch,
-                       "launch_pipeline": "launches of a step alternate between two forked streams" if n > frames_per_launch
-                       and os.environ.get("PSXB200_DEVICE_PIPELINE", "1") != "0" else "one stream",
-                       "l2": "inputs larger than L2 (%.0f MB of frames per step per GPU)" % (n * wl.frame_bytes / 1e6),
-                       "quant_scale_mean": float(res[:, 2].mean()), "parity_spot_check": True,
-                       "collective": "all_gather of per-frame results on a side stream" if world > 1 else "none"},
+            "config": headline_config(args.fdct),
+            "config_detail": {"frames_per_launch": frames_per_launch,
+                              "launch_pipeline": "launches of a step alternate between two forked streams" if n > frames_per_launch
+                              and os.environ.get("PSXB200_DEVICE_PIPELINE", "1") != "0" else "one stream",
+                              "quant_scale_mean": float(res[:, 2].mean()), "parity_spot_check": True,
+                              "collective": "all_gather of per-frame results on a side stream" if world > 1 else "none"},
             "sustained": {"value": world * n * sus_passes / (sus_ms / 1000.0), "unit": UNIT, "passes": sus_passes,
                           "seconds": sus_ms / 1000.0},
             "roofline": {"bound": "hbm", "kernel": "bs_dct_kernel + bs_pack_kernel (whole step)", "achieved": whole,
