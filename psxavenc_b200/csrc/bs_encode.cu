@@ -854,12 +854,13 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 				}
 			}
 			int prev = 0;
+			const unsigned long long signs = ((unsigned long long)meta.y << 32) | meta.x;   // by zig-zag position
 			// one coefficient: y at zig-zag position pos (mdec.c:484-499)
 			auto put_coef = [&](uint32_t y, int pos) {
 				const uint32_t lvl = __umulhi(y + qs.q, qs.m_hi);
 				const int run = pos - prev - 1;
 				prev = pos;
-				const uint32_t neg = (pos & 32 ? meta.y >> (pos & 31) : meta.x >> pos) & 1u;
+				const uint32_t neg = (uint32_t)(signs >> pos) & 1u;
 				const uint32_t code = s.vlc[min(lvl, (uint32_t)(BS_VLC_ROWS - 1)) * BS_VLC_COLS + min(run, BS_VLC_COLS - 1)];
 				if (code & 0xFFFFFFu) {
 					bw.put((int)(code >> 24), (code & 0xFFFFFFu) | neg);
