@@ -847,6 +847,7 @@ def bench_vagi(ctx, files):
            "ms_per_step": ms / passes,
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": ctx.peak, "unit": "GB/s", "frac": gbs / ctx.peak,
                         "algorithmic_bytes_per_sample": bytes_per_sample,
+                        "traffic": load_traffic().get("adpcm_spu_kernel") if files == 1024 else None,
                         "note": "ALU/issue bound by design (SURVEY.md 8d: ~375 integer ops per sample, ceiling ~1e5 Msamples/s "
                                 "per GPU with >= 1e4 chains); one chain runs 28 samples per ~1.3 us",
                         "frac_of_alu_ceiling": value / ctx.world / 1.0e5}}

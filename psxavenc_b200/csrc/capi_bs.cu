@@ -714,7 +714,9 @@ extern "C" int psxb200_strcd_encode_host(psxb200_bs_encoder_t *enc, int n_files,
 	// Files per chunk: a chunk's XA chains take their full serial latency (72 units per sector and
 	// channel) however few files it holds, so chunks are made large enough — four host chunks,
 	// 1024 frames by default — for the copies of the next chunk to cover it.
-	const int group = std::max(1, std::min(n_files, 4 * enc->host_chunk / frames_per_file));
+	int group_frames = 4 * enc->host_chunk;
+	if (const char *env = getenv("PSXB200_STRCD_GROUP_FRAMES")) group_frames = std::max(1, atoi(env));
+	const int group = std::max(1, std::min(n_files, group_frames / frames_per_file));
 	const int bound = str_max_budget(batch);
 	struct Pending { int file0, files; };
 	Pending pending[BS_SLOTS] = {};
