@@ -86,6 +86,7 @@ int psxb200::spu_encode_host_subset(int n_streams, int first, int step, const in
 	std::lock_guard<std::mutex> guard(ctx->lock);
 	if (ctx->ensure()) return -1;
 	cudaStream_t st = ctx->stream;
+	StreamDrain drain(st);
 	const long block_bytes = 16L * ((sample_count + 27) / 28);
 	const int n_sub = (n_streams - first + step - 1) / step;
 
@@ -106,6 +107,7 @@ int psxb200::spu_encode_host_subset(int n_streams, int first, int step, const in
 		                        d_base + in_bytes + 32, block_bytes, st));
 		g_launches += 1;
 		CU_TRY(cudaStreamSynchronize(st));
+		drain.armed = false;
 		memcpy(h_out, s_out, (size_t)block_bytes);
 		memcpy(h_states, s_state, STATE_BYTES);
 		return 0;
@@ -133,6 +135,7 @@ int psxb200::spu_encode_host_subset(int n_streams, int first, int step, const in
 	CU_TRY(cudaMemcpy2DAsync(hs + (size_t)first * STATE_BYTES, (size_t)step * STATE_BYTES, ctx->states.ptr + (size_t)first * STATE_BYTES,
 	                         (size_t)step * STATE_BYTES, STATE_BYTES, n_sub, cudaMemcpyDeviceToHost, st));
 	CU_TRY(cudaStreamSynchronize(st));
+	drain.armed = false;
 	return 0;
 }
 
@@ -187,6 +190,7 @@ extern "C" int psxb200_xa_encode_host(int n_streams, int format, int stereo, int
 	std::lock_guard<std::mutex> guard(ctx->lock);
 	if (ctx->ensure()) return -1;
 	cudaStream_t st = ctx->stream;
+	StreamDrain drain(st);
 
 	const long extent = adpcm_xa_input_extent(stereo, bits_per_sample, sample_count);
 	const long dstride_in = (long)round_up((size_t)extent, 8);
@@ -212,6 +216,7 @@ extern "C" int psxb200_xa_encode_host(int n_streams, int format, int stereo, int
 	                         cudaMemcpyDeviceToHost, st));
 	CU_TRY(cudaMemcpyAsync(h_states, ctx->states.ptr, (size_t)n_streams * 2 * STATE_BYTES, cudaMemcpyDeviceToHost, st));
 	CU_TRY(cudaStreamSynchronize(st));
+	drain.armed = false;
 	return (int)bytes;
 }
 

@@ -302,6 +302,24 @@ static int slot_prepare(psxb200_bs_encoder *enc, BsSlot &s) {
 
 namespace {
 
+// Early (error) return of a host entry point: waits for whatever the slots still have in flight.
+// Those copies read and write the caller's buffers, which it may release once the call is back.
+struct SlotDrain {
+	psxb200_bs_encoder *enc;
+	bool armed = true;
+	explicit SlotDrain(psxb200_bs_encoder *e) : enc(e) {}
+	~SlotDrain() {
+		if (!armed) return;
+		for (BsSlot &s : enc->slots) {
+			if (s.stream) cudaStreamSynchronize(s.stream);
+			if (s.audio_stream) cudaStreamSynchronize(s.audio_stream);
+		}
+		cudaGetLastError();
+	}
+	SlotDrain(const SlotDrain &) = delete;
+	SlotDrain &operator=(const SlotDrain &) = delete;
+};
+
 // One chunk of psxb200_bs_encode_host in flight on a slot.
 struct BsChunk {
 	int first = 0, m = 0, bound = 0;
@@ -323,6 +341,7 @@ extern "C" int psxb200_bs_encode_host(psxb200_bs_encoder_t *enc, int n, const ui
 	for (int i = 0; i < n; i++)
 		if (n > 1 && (size_t)std::max(h_max_sizes[i], 0) > out_stride)
 			return fail("psxb200_bs_encode_host: frame_max_size %d of frame %d > out_stride", h_max_sizes[i], i);
+	SlotDrain drain(enc);
 
 	// Chunks of host_chunk frames rotate through BS_SLOTS streams. A chunk goes through two
 	// phases: (A) frames in, kernels, result rows out; (B) once the rows are on the host, only
@@ -415,6 +434,7 @@ extern "C" int psxb200_bs_encode_host(psxb200_bs_encoder_t *enc, int n, const ui
 	if (phase_b((chunk - 1) % BS_SLOTS)) return -1;
 	for (int slot = 0; slot < BS_SLOTS; slot++)
 		if (finish(slot)) return -1;
+	drain.armed = false;
 	int failed = 0;
 	for (int i = 0; i < n; i++) failed += h_results[i].quant_scale >= 64;
 	return failed;
@@ -543,6 +563,7 @@ extern "C" int psxb200_str_encode_host_ex(psxb200_bs_encoder_t *enc, int n, cons
 	CU_TRY(guard.status);
 	for (BsSlot &s : enc->slots)
 		if (slot_prepare(enc, s)) return -1;
+	SlotDrain drain(enc);
 
 	const int hc = enc->host_chunk;
 	const int ss = batch.sector_size;
@@ -640,6 +661,7 @@ extern "C" int psxb200_str_encode_host_ex(psxb200_bs_encoder_t *enc, int n, cons
 	}
 	for (int slot = 0; slot < BS_SLOTS; slot++)
 		if (finish(slot)) return -1;
+	drain.armed = false;
 	int failed = 0;
 	for (int i = 0; i < n; i++) failed += h_results[i].quant_scale >= 64;
 	return failed;
@@ -694,6 +716,7 @@ extern "C" int psxb200_strcd_encode_host(psxb200_bs_encoder_t *enc, int n_files,
 	}
 	const uint32_t *edc = edc_tables_device();
 	if (!edc) return fail("psxb200_strcd_encode_host: EDC tables unavailable");
+	SlotDrain drain(enc);
 
 	const int ss = batch.sector_size;
 	const int xa_format = p.format == FORMAT_STRCD ? 1 : 0;
@@ -788,6 +811,7 @@ extern "C" int psxb200_strcd_encode_host(psxb200_bs_encoder_t *enc, int n_files,
 	}
 	for (int slot = 0; slot < BS_SLOTS; slot++)
 		if (finish(slot)) return -1;
+	drain.armed = false;
 	int failed = 0;
 	for (long long i = 0; i < (long long)n_files * frames_per_file; i++) failed += h_results[i].quant_scale >= 64;
 	return failed;

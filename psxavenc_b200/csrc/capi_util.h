@@ -52,6 +52,21 @@ struct DeviceGuard {
 	DeviceGuard &operator=(const DeviceGuard &) = delete;
 };
 
+// Error return of a host entry point with copies still queued on `stream`: they touch the
+// caller's buffers, so the stream is drained before the call goes back.
+struct StreamDrain {
+	cudaStream_t stream;
+	bool armed = true;
+	explicit StreamDrain(cudaStream_t st) : stream(st) {}
+	~StreamDrain() {
+		if (!armed) return;
+		cudaStreamSynchronize(stream);
+		cudaGetLastError();
+	}
+	StreamDrain(const StreamDrain &) = delete;
+	StreamDrain &operator=(const StreamDrain &) = delete;
+};
+
 template <typename T>
 struct DeviceBuffer {
 	T *ptr = nullptr;
