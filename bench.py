@@ -990,7 +990,9 @@ def run_ours(args):
     configs = {}
     legs = [("strv_easy", lambda: bench_content(ctx, 0, "easy")), ("strv_hard", lambda: bench_content(ctx, 6, "hard")),
             ("sbs", lambda: bench_sbs(ctx)), ("strcd", lambda: bench_strcd(ctx)),
-            ("vagi_x1024", lambda: bench_vagi(ctx, 1024)), ("vagi_x1", lambda: bench_vagi(ctx, 1))]
+            ("vagi_x1024", lambda: bench_vagi(ctx, 1024)), ("vagi_x1", lambda: bench_vagi(ctx, 1)),
+            # the rest of SURVEY.md 8d's B set: x64 leaves most SMs idle, x4096 is the kernel with the machine full
+            ("vagi_x64", lambda: bench_vagi(ctx, 64)), ("vagi_x4096", lambda: bench_vagi(ctx, 4096))]
     if args.only:
         legs = [l for l in legs if l[0] in args.only.split(",")]
     for name, fn in legs:
