@@ -15,6 +15,8 @@
 //   xa_frame_kernel    sector sync/header/subheader (adpcm.c:266-291, cdrom.c:55-74) and the
 //                      EDC CRC (cdrom.c:30-41, 102-109), one thread per sector
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 #include <stdint.h>
 
 #include "adpcm_encode.h"
@@ -206,14 +208,15 @@ adpcm_spu_kernel(int n_streams, int stream_first, int stream_step, const int16_t
 
 // ---- XA ----------------------------------------------------------------------------------
 
-template <int BITS, bool STEREO>   // 4 or 8 bits per sample; mono and stereo are compiled separately
-__global__ void __launch_bounds__(ADPCM_THREADS, 8)
+// 4 or 8 bits per sample; mono and stereo are compiled separately; WARPS per CTA: 4 spreads the
+// chains over the machine, 16 packs them onto few SMs (see adpcm_launch_xa)
+template <int BITS, bool STEREO, int WARPS, int MIN_CTAS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 adpcm_xa_kernel(int n_streams, int sector_size, long sector_stride, const int16_t *__restrict__ samples, long in_stride,
                 int sample_count, ChannelState *__restrict__ states, uint8_t *__restrict__ out, long out_stride) {
 	constexpr int RANGE = BITS == 4 ? 12 : 8;
 	constexpr int UNITS = BITS == 4 ? 8 : 4;        // units per 128-byte sound group
 	constexpr int JUMP = BITS == 4 ? 224 : 112;     // interleaved samples per sound group
-	constexpr int WARPS = ADPCM_THREADS / 32;
 	// unit codes, one byte per sample, and unit headers: one set per stream of the warp
 	constexpr bool stereo = STEREO;
 	constexpr int SETS = STEREO ? 1 : 2;
@@ -410,14 +413,30 @@ cudaError_t adpcm_launch_xa(int n_streams, int format, int stereo, int frequency
 	if (n_streams <= 0 || sectors == 0) return cudaSuccess;
 	int sector_size = format == 0 ? 2336 : 2352;
 	if (sector_stride <= 0) sector_stride = sector_size;
-	constexpr int WARPS = ADPCM_THREADS / 32;
 	const int warps = stereo ? n_streams : (n_streams + 1) / 2;   // a warp takes two mono streams
-	unsigned grid = (unsigned)((warps + WARPS - 1) / WARPS);
-	auto kern = bits_per_sample == 8 ? (stereo ? adpcm_xa_kernel<8, true> : adpcm_xa_kernel<8, false>)
-	                                 : (stereo ? adpcm_xa_kernel<4, true> : adpcm_xa_kernel<4, false>);
-	kern<<<grid, ADPCM_THREADS, 0, stream>>>(n_streams, sector_size, sector_stride, d_samples, in_stride, sample_count,
-	                                         static_cast<ChannelState *>(d_states), d_out, out_stride);
-	cudaError_t e = cudaGetLastError();
+	// Two shapes (profiles/r2_xa_shape_ab.txt). Spread: 4 warps per CTA, one chain-pair per scheduler on
+	// as many SMs as there are CTAs — lowest latency when the chains have the machine to themselves.
+	// Packed: 8 warps per CTA at 127 registers, used when the sectors go into a muxed image (a sector
+	// stride that leaves room for other sectors), i.e. when the video kernels of the same files run
+	// beside the chains: they then crowd half as many SMs and the two kernels overlap far better
+	// (512 files x 8 frames + 10 XA sectors: 1.93 -> 1.59 ms per step) at 15 % more latency alone.
+	const bool packed = sector_stride > sector_size;
+	cudaError_t e = cudaSuccess;
+	auto launch = [&](auto kern, int W) {
+		unsigned grid = (unsigned)((warps + W - 1) / W);
+		kern<<<grid, W * 32, 0, stream>>>(n_streams, sector_size, sector_stride, d_samples, in_stride, sample_count,
+		                                  static_cast<ChannelState *>(d_states), d_out, out_stride);
+	};
+#define PSXB200_XA_LAUNCH(W, M)                                                                       \
+	do {                                                                                              \
+		if (bits_per_sample == 8) { if (stereo) launch(adpcm_xa_kernel<8, true, W, M>, W); else launch(adpcm_xa_kernel<8, false, W, M>, W); } \
+		else { if (stereo) launch(adpcm_xa_kernel<4, true, W, M>, W); else launch(adpcm_xa_kernel<4, false, W, M>, W); }                     \
+	} while (0)
+	if (packed) PSXB200_XA_LAUNCH(8, 1);
+	else PSXB200_XA_LAUNCH(4, 4);
+#undef PSXB200_XA_LAUNCH
+	if (e != cudaSuccess) return e;
+	e = cudaGetLastError();
 	if (e != cudaSuccess || !d_edc_tables) return e;
 	int coding = (stereo ? 1 : 0) | (frequency == 37800 ? 0 : 4) | (bits_per_sample == 8 ? 16 : 0);
 	long n = (long)n_streams * sectors;
