@@ -26,9 +26,12 @@ constexpr size_t ZERO_COPY_BYTES = 16 * 1024;
 
 // Context of the host-pointer audio entry points, one per device (the reference API has no
 // handle to hang it on: libpsxav.h:78-101).
+constexpr int SPU_PIPE_STREAMS = 4;   // chunks of a large SPU call in flight (copy in | kernel | copy out)
+
 struct AudioContext {
 	std::mutex lock;
 	cudaStream_t stream = nullptr;
+	cudaStream_t pipe[SPU_PIPE_STREAMS] = {};   // pipe[0] is `stream`
 	DeviceBuffer<int16_t> in;
 	DeviceBuffer<uint8_t> out;
 	DeviceBuffer<uint8_t> states;
@@ -36,6 +39,9 @@ struct AudioContext {
 	const uint32_t *edc = nullptr;
 	int ensure() {
 		if (!stream) CU_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+		pipe[0] = stream;
+		for (int i = 1; i < SPU_PIPE_STREAMS; i++)
+			if (!pipe[i]) CU_TRY(cudaStreamCreateWithFlags(&pipe[i], cudaStreamNonBlocking));
 		if (!edc) {
 			edc = edc_tables_device();
 			if (!edc) return fail("EDC tables unavailable: %s", cudaGetErrorString(cudaGetLastError()));
@@ -124,6 +130,44 @@ int psxb200::spu_encode_host_subset(int n_streams, int first, int step, const in
 	CU_TRY(ctx->in.reserve((size_t)extent));
 	CU_TRY(ctx->out.reserve((size_t)n_streams * dstride));
 	CU_TRY(ctx->states.reserve((size_t)n_streams * STATE_BYTES));
+
+	// Many whole interleave groups that do not overlap in memory (vagi x B): the call is cut into
+	// runs of groups that rotate over SPU_PIPE_STREAMS streams, so that the copy-in of a run
+	// overlaps the kernel and the copy-out of the runs before it. A chain is sequential in time
+	// (adpcm.c:135-136, 186-190), its kernel takes ~45 ns per sample however few chains a launch
+	// holds; about a thousand chains per run keep the host->device link busy meanwhile.
+	const int n_groups = (n_streams + pitch - 1) / pitch;
+	if (first == 0 && step == 1 && n_groups >= 2 && group_stride >= (long)pitch * sample_count) {
+		const long chain_bytes = (long)sample_count * 2;
+		const long run_chains = std::max(1024L, (4L << 20) / chain_bytes);
+		const int run_groups = (int)std::max(1L, (run_chains + pitch - 1) / pitch);
+		if (n_groups >= 2 * run_groups) {
+			StreamDrain drains[SPU_PIPE_STREAMS - 1] = {StreamDrain(ctx->pipe[1]), StreamDrain(ctx->pipe[2]), StreamDrain(ctx->pipe[3])};
+			int k = 0;
+			for (int g0 = 0; g0 < n_groups; g0 += run_groups, k++) {
+				const int g1 = std::min(n_groups, g0 + run_groups);
+				const int s0 = g0 * pitch, s1 = std::min(n_streams, g1 * pitch);
+				const long lo = (long)g0 * group_stride;
+				const long hi = g1 == n_groups ? extent : (long)g1 * group_stride;
+				cudaStream_t ps = ctx->pipe[k % SPU_PIPE_STREAMS];
+				CU_TRY(cudaMemcpyAsync(ctx->in.ptr + lo, h_samples + lo, (size_t)(hi - lo) * sizeof(int16_t), cudaMemcpyHostToDevice, ps));
+				CU_TRY(cudaMemcpyAsync(ctx->states.ptr + (size_t)s0 * STATE_BYTES, hs + (size_t)s0 * STATE_BYTES,
+				                       (size_t)(s1 - s0) * STATE_BYTES, cudaMemcpyHostToDevice, ps));
+				CU_TRY(adpcm_launch_spu(s1 - s0, ctx->in.ptr + lo, pitch, group_stride, sample_count, nullptr,
+				                        ctx->states.ptr + (size_t)s0 * STATE_BYTES, ctx->out.ptr + (size_t)s0 * dstride, dstride, ps));
+				g_launches += 1;
+				CU_TRY(cudaMemcpy2DAsync(h_out + (size_t)s0 * h_pitch, h_pitch, ctx->out.ptr + (size_t)s0 * dstride, (size_t)dstride,
+				                         (size_t)block_bytes, (size_t)(s1 - s0), cudaMemcpyDeviceToHost, ps));
+				CU_TRY(cudaMemcpyAsync(hs + (size_t)s0 * STATE_BYTES, ctx->states.ptr + (size_t)s0 * STATE_BYTES,
+				                       (size_t)(s1 - s0) * STATE_BYTES, cudaMemcpyDeviceToHost, ps));
+			}
+			for (int i = 0; i < SPU_PIPE_STREAMS; i++) CU_TRY(cudaStreamSynchronize(ctx->pipe[i]));
+			drain.armed = false;
+			for (auto &d : drains) d.armed = false;
+			return 0;
+		}
+	}
+
 	CU_TRY(cudaMemcpyAsync(ctx->in.ptr, h_samples, (size_t)extent * sizeof(int16_t), cudaMemcpyHostToDevice, st));
 	CU_TRY(cudaMemcpy2DAsync(ctx->states.ptr + (size_t)first * STATE_BYTES, (size_t)step * STATE_BYTES, hs + (size_t)first * STATE_BYTES,
 	                         (size_t)step * STATE_BYTES, STATE_BYTES, n_sub, cudaMemcpyHostToDevice, st));
