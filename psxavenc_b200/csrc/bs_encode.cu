@@ -361,6 +361,36 @@ __device__ __forceinline__ int ac_bits(const uint4 *__restrict__ gp, int nrows, 
 	return (int)bits;
 }
 
+// The first pass (q = 1): every list entry is a coefficient (y >= 1), so its level is (y + 1) >> 1
+// without a division and its run is the distance to the entry walked before it — padding entries
+// (all zero, walked first) cost the guard byte and leave the position at 0.
+template <bool UPPER>
+__device__ __forceinline__ void price_entry_q1(uint32_t word, const uint8_t *lenlut1, uint32_t &bits, uint32_t &prev) {
+	const uint32_t e = UPPER ? word >> 16 : word & 0xFFFFu;
+	const uint32_t pos = e & 63u;
+	const uint32_t row = min(((e + 64u) >> 1) & 0xFFC0u, 63u << 6);   // 64 * min(level, 63)
+	bits += lenlut1[row + pos - prev];
+	prev = pos;
+}
+
+__device__ __forceinline__ int ac_bits_q1(const uint4 *__restrict__ gp, int nrows, const uint8_t *lenlut1) {
+	uint32_t bits = 0, prev = 0;
+	uint4 next = gp[(nrows > 0 ? nrows - 1 : 0) * 32];
+	for (int r = nrows - 1; r >= 0; r--) {
+		const uint4 w = next;
+		next = gp[(r > 0 ? r - 1 : 0) * 32];
+		price_entry_q1<true>(w.w, lenlut1, bits, prev);
+		price_entry_q1<false>(w.w, lenlut1, bits, prev);
+		price_entry_q1<true>(w.z, lenlut1, bits, prev);
+		price_entry_q1<false>(w.z, lenlut1, bits, prev);
+		price_entry_q1<true>(w.y, lenlut1, bits, prev);
+		price_entry_q1<false>(w.y, lenlut1, bits, prev);
+		price_entry_q1<true>(w.x, lenlut1, bits, prev);
+		price_entry_q1<false>(w.x, lenlut1, bits, prev);
+	}
+	return (int)bits;
+}
+
 // The same for a dense group (all 64 y values in zig-zag order, position implicit), one half
 // (four rows, 32 positions) at a time to bound the register footprint.
 template <int HALF>
@@ -735,7 +765,9 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 			if (b >= 0) {
 				const uint4 *gp = fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane;
 				const int rows = s.grows[g];
-				bits = (rows & 0x80) ? ac_bits_dense(gp, qs, s.lenlut) : ac_bits(gp, rows, qs, s.lenlut - 1);
+				// the first pass has its own list walk (measured: -2.9 % of the kernel on q = 2 content)
+				if (!BUSY && q == 1 && !(rows & 0x80)) bits = ac_bits_q1(gp, rows, s.lenlut - 1);
+				else bits = (rows & 0x80) ? ac_bits_dense(gp, qs, s.lenlut) : ac_bits(gp, rows, qs, s.lenlut - 1);
 				bits += 2 + (V3 ? (int)(dc_code(b) >> 24) : 10);
 				s.lens[b] = (uint16_t)bits;
 			}
