@@ -46,8 +46,10 @@ namespace psxb200 {
 // [q] -> reciprocals of the pass's common divisor: .x = floor(2^32 / 2q) + 1 for t = y + q,
 // .y = floor(2^32 / 128q) + 1 for t = 64 (y + q) + (any 6 low bits); level = umulhi(t, magic).
 __constant__ uint2 c_qmagic[64];
-// [min(level,63)][run] -> code length in bits incl. sign (22 = escape), 0 for level 0.
-__constant__ uint8_t c_lenlut[64 * 64];
+// One zero guard byte, then [min(level,63)][run] -> code length in bits incl. sign (22 = escape),
+// 0 for level 0 (the list walks index it with run + 1, see price_entry); padded to whole words.
+constexpr int LENLUT1_BYTES = 4 + 64 * 64;
+__constant__ uint8_t c_lenlut1[LENLUT1_BYTES];
 // [min(level,41)][min(run,32)] -> (len << 24) | code with the sign bit (LSB) clear; level 0 -> 0;
 // escape (including all of row 41 and column 32) -> (22 << 24) with code 0. Copied to shared
 // memory by every CTA.
@@ -86,7 +88,7 @@ cudaError_t bs_upload_tables() {
 	if (g_tables_uploaded[dev]) return cudaSuccess;
 
 	static uint2 qmagic[64];
-	static uint8_t lenlut[64 * 64];
+	static uint8_t lenlut1[LENLUT1_BYTES];
 	static uint32_t vlc[BS_VLC_ROWS * BS_VLC_COLS];
 	static uint32_t dcvlc[2 * 512];
 	static uint32_t edc[EDC_TABLE_WORDS];
@@ -102,7 +104,7 @@ cudaError_t bs_upload_tables() {
 				uint32_t e = (run < BS_AC_RUNS && lv < BS_AC_LEVELS) ? BS_AC_VLC[run * BS_AC_LEVELS + lv] : 0;
 				len = e ? (int)(e >> 24) : BS_AC_ESCAPE_BITS;
 			}
-			lenlut[(lv << 6) | run] = (uint8_t)len;
+			lenlut1[1 + ((lv << 6) | run)] = (uint8_t)len;
 			uint32_t e = (lv > 0 && run < BS_AC_RUNS && lv < BS_AC_LEVELS) ? BS_AC_VLC[run * BS_AC_LEVELS + lv] : 0;
 			if (lv < BS_VLC_ROWS && run < BS_VLC_COLS)
 				vlc[lv * BS_VLC_COLS + run] = lv == 0 ? 0u : (e ? e : (uint32_t)BS_AC_ESCAPE_BITS << 24);
@@ -119,7 +121,7 @@ cudaError_t bs_upload_tables() {
 	// once per device, before any kernel of this library has been launched on it.
 	if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
 	if ((e = cudaMemcpyToSymbol(c_qmagic, qmagic, sizeof(qmagic))) != cudaSuccess) return e;
-	if ((e = cudaMemcpyToSymbol(c_lenlut, lenlut, sizeof(lenlut))) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(c_lenlut1, lenlut1, sizeof(lenlut1))) != cudaSuccess) return e;
 	if ((e = cudaMemcpyToSymbol(g_vlc, vlc, sizeof(vlc))) != cudaSuccess) return e;
 	if ((e = cudaMemcpyToSymbol(c_dcvlc, dcvlc, sizeof(dcvlc))) != cudaSuccess) return e;
 	if ((e = cudaMemcpyToSymbol(g_edc, edc, sizeof(edc))) != cudaSuccess) return e;
@@ -286,7 +288,8 @@ struct PackSmem {
 	uint32_t *vlc;      // [min(level,41)][min(run,32)] -> (len<<24)|code, see g_vlc
 	uint16_t *lens;     // per block bit length at the current q; after the scan: exclusive offset in its group
 	int16_t *dcval;     // v3: per block quantised DC, replaced in place by its coded delta
-	uint8_t *lenlut;    // [min(level,63)][run] -> code length; preceded by 16 zero guard bytes (see price_entry)
+	uint8_t *lenlut;    // [min(level,63)][run] -> code length; preceded by a zero guard byte (see price_entry)
+	uint32_t lut1;      // shared-space address of that guard byte (lenlut - 1), a multiple of 64
 	uint32_t *stage;    // emit: up to four list rows of the thread's current block, word j at stage[j * T + tid]
 };
 
@@ -331,32 +334,40 @@ __device__ __forceinline__ uint32_t entry_pos(uint32_t word) {
 	return UPPER ? (word >> 16) & 63u : word & 63u;
 }
 
-// lenlut1 = the length table minus one byte: run = pos - prev - 1, and a padding entry (level 0,
-// position 0, met only while prev is still 0) reads the zero guard byte in front of the table.
+__device__ __forceinline__ uint32_t lds_u8(uint32_t shared_addr) {
+	uint32_t v;
+	asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(shared_addr));
+	return v;
+}
+
+// lut1 = the shared-space address of the byte in front of the length table: run = pos - prev - 1,
+// and a padding entry (level 0, position 0, met only while prev is still 0) reads that zero guard
+// byte. The table's address goes into the same three-input add as the run (the compiler, left with
+// a pointer, spent one more add per entry on it).
 template <bool UPPER>
-__device__ __forceinline__ void price_entry(uint32_t word, const QuantScale &k, const uint8_t *lenlut1, uint32_t &bits,
+__device__ __forceinline__ void price_entry(uint32_t word, const QuantScale &k, uint32_t lut1, uint32_t &bits,
                                             uint32_t &prev) {
 	const uint32_t lv = entry_level<UPPER>(word, k);
 	const uint32_t pos = entry_pos<UPPER>(word);
-	bits += lenlut1[imad(min(lv, 63u), 64u, pos) - prev];
+	bits += lds_u8(imad(min(lv, 63u), 64u, pos - prev + lut1));
 	prev = lv ? pos : prev;
 }
 
 // AC bit cost of the block whose list occupies rows 0..nrows-1 of (group, lane).
-__device__ __forceinline__ int ac_bits(const uint4 *__restrict__ gp, int nrows, const QuantScale &k, const uint8_t *lenlut1) {
+__device__ __forceinline__ int ac_bits(const uint4 *__restrict__ gp, int nrows, const QuantScale &k, uint32_t lut1) {
 	uint32_t bits = 0, prev = 0;
 	uint4 next = gp[(nrows > 0 ? nrows - 1 : 0) * 32];   // the row after this one is in flight while this one is priced
 	for (int r = nrows - 1; r >= 0; r--) {
 		const uint4 w = next;
 		next = gp[(r > 0 ? r - 1 : 0) * 32];
-		price_entry<true>(w.w, k, lenlut1, bits, prev);
-		price_entry<false>(w.w, k, lenlut1, bits, prev);
-		price_entry<true>(w.z, k, lenlut1, bits, prev);
-		price_entry<false>(w.z, k, lenlut1, bits, prev);
-		price_entry<true>(w.y, k, lenlut1, bits, prev);
-		price_entry<false>(w.y, k, lenlut1, bits, prev);
-		price_entry<true>(w.x, k, lenlut1, bits, prev);
-		price_entry<false>(w.x, k, lenlut1, bits, prev);
+		price_entry<true>(w.w, k, lut1, bits, prev);
+		price_entry<false>(w.w, k, lut1, bits, prev);
+		price_entry<true>(w.z, k, lut1, bits, prev);
+		price_entry<false>(w.z, k, lut1, bits, prev);
+		price_entry<true>(w.y, k, lut1, bits, prev);
+		price_entry<false>(w.y, k, lut1, bits, prev);
+		price_entry<true>(w.x, k, lut1, bits, prev);
+		price_entry<false>(w.x, k, lut1, bits, prev);
 	}
 	return (int)bits;
 }
@@ -364,29 +375,33 @@ __device__ __forceinline__ int ac_bits(const uint4 *__restrict__ gp, int nrows, 
 // The first pass (q = 1): every list entry is a coefficient (y >= 1), so its level is (y + 1) >> 1
 // without a division and its run is the distance to the entry walked before it — padding entries
 // (all zero, walked first) cost the guard byte and leave the position at 0.
+// lut1x2 = 64 + twice the table's address, lut1max = the address of its last row: with the address a
+// multiple of 64 it rides through the shift and the mask, ((e + 64 + 2 lut1) >> 1) & ~63 =
+// 64 * level + lut1.
 template <bool UPPER>
-__device__ __forceinline__ void price_entry_q1(uint32_t word, const uint8_t *lenlut1, uint32_t &bits, uint32_t &prev) {
+__device__ __forceinline__ void price_entry_q1(uint32_t word, uint32_t lut1x2, uint32_t lut1max, uint32_t &bits, uint32_t &prev) {
 	const uint32_t e = UPPER ? word >> 16 : word & 0xFFFFu;
 	const uint32_t pos = e & 63u;
-	const uint32_t row = min(((e + 64u) >> 1) & 0xFFC0u, 63u << 6);   // 64 * min(level, 63)
-	bits += lenlut1[row + pos - prev];
+	const uint32_t row = min(((e + lut1x2) >> 1) & ~63u, lut1max);   // lut1 + 64 * min(level, 63)
+	bits += lds_u8(row + pos - prev);
 	prev = pos;
 }
 
-__device__ __forceinline__ int ac_bits_q1(const uint4 *__restrict__ gp, int nrows, const uint8_t *lenlut1) {
+__device__ __forceinline__ int ac_bits_q1(const uint4 *__restrict__ gp, int nrows, uint32_t lut1) {
 	uint32_t bits = 0, prev = 0;
+	const uint32_t lut1x2 = 64u + 2u * lut1, lut1max = lut1 + (63u << 6);
 	uint4 next = gp[(nrows > 0 ? nrows - 1 : 0) * 32];
 	for (int r = nrows - 1; r >= 0; r--) {
 		const uint4 w = next;
 		next = gp[(r > 0 ? r - 1 : 0) * 32];
-		price_entry_q1<true>(w.w, lenlut1, bits, prev);
-		price_entry_q1<false>(w.w, lenlut1, bits, prev);
-		price_entry_q1<true>(w.z, lenlut1, bits, prev);
-		price_entry_q1<false>(w.z, lenlut1, bits, prev);
-		price_entry_q1<true>(w.y, lenlut1, bits, prev);
-		price_entry_q1<false>(w.y, lenlut1, bits, prev);
-		price_entry_q1<true>(w.x, lenlut1, bits, prev);
-		price_entry_q1<false>(w.x, lenlut1, bits, prev);
+		price_entry_q1<true>(w.w, lut1x2, lut1max, bits, prev);
+		price_entry_q1<false>(w.w, lut1x2, lut1max, bits, prev);
+		price_entry_q1<true>(w.z, lut1x2, lut1max, bits, prev);
+		price_entry_q1<false>(w.z, lut1x2, lut1max, bits, prev);
+		price_entry_q1<true>(w.y, lut1x2, lut1max, bits, prev);
+		price_entry_q1<false>(w.y, lut1x2, lut1max, bits, prev);
+		price_entry_q1<true>(w.x, lut1x2, lut1max, bits, prev);
+		price_entry_q1<false>(w.x, lut1x2, lut1max, bits, prev);
 	}
 	return (int)bits;
 }
@@ -674,7 +689,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
                const int *__restrict__ max_sizes, int max_size_bound, uint8_t *__restrict__ out, size_t out_stride,
                psxb200_bs_result_t *__restrict__ results, uint32_t *__restrict__ gstream, size_t gstream_stride,
                const BsStrLayout str) {
-	extern __shared__ __align__(16) uint8_t smem_raw[];
+	extern __shared__ __align__(128) uint8_t smem_raw[];
 	const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
 	const int f = blockIdx.x;
 	if (BUSY && results[f].quant_scale != 0) return;   // finished by the first kernel
@@ -686,7 +701,9 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	{
 		uint8_t *p = smem_raw;
 		auto take = [&](size_t bytes) { uint8_t *at = p; p += (bytes + 15) & ~(size_t)15; return at; };
-		s.lenlut = take(16 + 64 * 64) + 16;
+		s.lenlut = take(LENLUT1_BYTES) + 1;
+		s.lut1 = (uint32_t)__cvta_generic_to_shared(s.lenlut - 1);
+		if (s.lut1 & 63u) __trap();   // the q = 1 walk relies on it (ac_bits_q1)
 		s.vlc = reinterpret_cast<uint32_t *>(take(4 * BS_VLC_ROWS * BS_VLC_COLS));
 		s.misc = reinterpret_cast<uint32_t *>(take(4 * (8 + 4 * 32)));
 		s.stream = reinterpret_cast<uint32_t *>(SMEM_STREAM ? take(4 * (size_t)stream_words) : p);
@@ -712,9 +729,8 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	if (max_size > max_size_bound) max_size = 0;   // contract violation -> frame fails
 	const int words = max_size > 0 ? (max_size + 3) / 4 + 2 : 0;
 
-	for (int i = tid; i < 64 * 64 / 4; i += T)
-		reinterpret_cast<uint32_t *>(s.lenlut)[i] = reinterpret_cast<const uint32_t *>(c_lenlut)[i];
-	if (tid < 4) reinterpret_cast<uint32_t *>(s.lenlut - 16)[tid] = 0;
+	for (int i = tid; i < LENLUT1_BYTES / 4; i += T)
+		reinterpret_cast<uint32_t *>(s.lenlut - 1)[i] = reinterpret_cast<const uint32_t *>(c_lenlut1)[i];
 	for (int i = tid; i < BS_VLC_ROWS * BS_VLC_COLS; i += T) s.vlc[i] = g_vlc[i];
 	if (V3) for (int i = tid; i < 1024; i += T) s.dctab[i] = c_dcvlc[i];
 	for (int i = tid; i < words; i += T) stream[i] = 0;
@@ -766,8 +782,8 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 				const uint4 *gp = fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane;
 				const int rows = s.grows[g];
 				// the first pass has its own list walk (measured: -2.9 % of the kernel on q = 2 content)
-				if (!BUSY && q == 1 && !(rows & 0x80)) bits = ac_bits_q1(gp, rows, s.lenlut - 1);
-				else bits = (rows & 0x80) ? ac_bits_dense(gp, qs, s.lenlut) : ac_bits(gp, rows, qs, s.lenlut - 1);
+				if (!BUSY && q == 1 && !(rows & 0x80)) bits = ac_bits_q1(gp, rows, s.lut1);
+				else bits = (rows & 0x80) ? ac_bits_dense(gp, qs, s.lenlut) : ac_bits(gp, rows, qs, s.lut1);
 				bits += 2 + (V3 ? (int)(dc_code(b) >> 24) : 10);
 				s.lens[b] = (uint16_t)bits;
 			}
@@ -976,7 +992,7 @@ size_t bs_pack_smem_bytes(bool v3, bool smem_stream, const BsGeometry &geo, int 
 	size_t padded = (size_t)geo.nsgroups * 32;
 	size_t n = 0;
 	auto take = [&](size_t bytes) { n += (bytes + 15) & ~(size_t)15; };
-	take(16 + 64 * 64);                   // guard + lenlut
+	take(LENLUT1_BYTES);                  // guard + lenlut
 	take(4 * BS_VLC_ROWS * BS_VLC_COLS);  // vlc
 	take(4 * (8 + 4 * 32));               // misc
 	if (smem_stream) take(4 * (size_t)((max_size_bound + 3) / 4 + 2));
