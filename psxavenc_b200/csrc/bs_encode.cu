@@ -438,6 +438,7 @@ __device__ __forceinline__ int ac_bits_dense(const uint4 *__restrict__ gp, const
 
 // Emit, convergent part for a dense group: parks rows 4*half..4*half+3 in the thread's column and
 // returns the mask of positions 32*half + e that are coefficients at this quant scale (bit e).
+template <bool PRED>
 __device__ __forceinline__ uint32_t stage_dense(const uint4 *__restrict__ gp, int half, const QuantScale &k,
                                                 uint32_t *stage, int stride) {
 	uint32_t live = 0;
@@ -449,8 +450,17 @@ __device__ __forceinline__ uint32_t stage_dense(const uint4 *__restrict__ gp, in
 #pragma unroll
 		for (int t = 0; t < 4; t++) {
 			stage[(4 * j + t) * stride] = w[t];
-			live |= ((w[t] & 0xFFFFu) >= k.q ? 1u : 0u) << (8 * j + 2 * t);
-			live |= (w[t] >= q16 ? 1u : 0u) << (8 * j + 2 * t + 1);
+			if (PRED) {
+				// compare + predicated add as in stage_rows — in the kernel for busy frames only: in
+				// the common kernel, where dense groups are rare, it cost the list path 1 % (measured)
+				asm("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, 1, %0;\n\t}"
+				    : "+r"(live) : "r"(w[t] & 0xFFFFu), "r"(k.q), "r"(1u << (8 * j + 2 * t)));
+				asm("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, 1, %0;\n\t}"
+				    : "+r"(live) : "r"(w[t]), "r"(q16), "r"(1u << (8 * j + 2 * t + 1)));
+			} else {
+				live |= ((w[t] & 0xFFFFu) >= k.q ? 1u : 0u) << (8 * j + 2 * t);
+				live |= (w[t] >= q16 ? 1u : 0u) << (8 * j + 2 * t + 1);
+			}
 		}
 	}
 	return live;
@@ -602,22 +612,27 @@ __device__ __forceinline__ int quant_dc(uint32_t mag, uint32_t negative) {
 // that is nonzero at q costs at least the run-0 code of its level (the shortest code of a level,
 // and lengths grow with the level), so  fixed + sum over entries of len(level(y, q), run 0)  is a
 // lower bound of the frame's bit total at q; capping y at 15 only lowers it further. One walk over
-// the lists builds a histogram of min(y, 15): each thread adds, per entry, a 128-bit word from a
-// 16-entry table that holds a one in the byte of the entry's bin (a block has at most 64 entries,
-// so the byte counters cannot overflow within a block), and unpacks the bytes into its 15
-// counters once per block. From the CTA-wide sums the bound follows for all q at once.
+// the lists builds a histogram of min(y, 15): each thread adds, per PAIR of entries (one 32-bit
+// word of a row), a 128-bit word from a 256-entry table that holds the two ones in the bytes of
+// the entries' bins (a block has at most 64 entries, so the byte counters cannot overflow within a
+// block), and unpacks the bytes into its 15 counters once per block. (One table read per entry from
+// a 16-entry table was bound by the shared-memory bandwidth of the 128-bit reads.) From the
+// CTA-wide sums the bound follows for all q at once.
 // Called by all threads of the CTA; returns the smallest q >= 2 the bound cannot exclude (64: none).
 constexpr int CENSUS_BINS = 15;
 
 __device__ __noinline__ int census_first_candidate(const uint4 *__restrict__ fc, int ngroups, int cpad, int nmb,
                                                    const uint8_t *grows, const uint8_t *lenlut,
-                                                   uint32_t *scratch /* >= 128 words */, int fixed_bits, int limit_bits) {
+                                                   uint32_t *scratch /* >= 64 words */, uint4 *pairtab /* 256 entries */,
+                                                   int fixed_bits, int limit_bits) {
 	const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
-	uint4 *onehot = reinterpret_cast<uint4 *>(scratch + 64);   // [min(y, 15)] -> a one in byte (bin - 1), zero for y = 0
-	if (tid < 16) {
+	// [min(y_lo, 15) | min(y_hi, 15) << 4] -> a one in byte (bin - 1) for each of the two, none for y = 0
+	for (int i = tid; i < 256; i += T) {
 		uint32_t w[4] = {0, 0, 0, 0};
-		if (tid) w[(tid - 1) >> 2] = 1u << (8 * ((tid - 1) & 3));
-		onehot[tid] = make_uint4(w[0], w[1], w[2], w[3]);
+		const int a = i & 15, b = i >> 4;
+		if (a) w[(a - 1) >> 2] += 1u << (8 * ((a - 1) & 3));
+		if (b) w[(b - 1) >> 2] += 1u << (8 * ((b - 1) & 3));
+		pairtab[i] = make_uint4(w[0], w[1], w[2], w[3]);
 	}
 	if (tid < 64) scratch[tid] = tid == CENSUS_BINS ? 64u : 0u;   // [0..14] bin totals, [15] the answer
 	__syncthreads();
@@ -631,18 +646,17 @@ __device__ __noinline__ int census_first_candidate(const uint4 *__restrict__ fc,
 		const bool dense = rows & 0x80;
 		const int nrows = dense ? 8 : rows;
 		uint4 acc = make_uint4(0, 0, 0, 0);
-		auto count = [&](uint32_t y) {
-			const uint4 one = onehot[min(y, (uint32_t)CENSUS_BINS)];
-			acc.x += one.x; acc.y += one.y; acc.z += one.z; acc.w += one.w;
-		};
 		for (int r = 0; r < nrows; r++) {
 			const uint4 w = gp[r * 32];
 			const uint32_t v[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
 			for (int t = 0; t < 4; t++) {
-				// dense rows hold bare y values, list rows (y << 6) | position
-				count(dense ? v[t] & 0xFFFFu : (v[t] & 0xFFFFu) >> 6);
-				count(dense ? v[t] >> 16 : v[t] >> 22);
+				// dense rows hold bare y values, list rows (y << 6) | position: both y of the word,
+				// capped at 15 in one packed minimum, then merged into lo | hi << 4
+				const uint32_t yy = dense ? v[t] : (v[t] >> 6) & 0x03FF03FFu;
+				const uint32_t m = __vminu2(yy, 0x000F000Fu);
+				const uint4 two = pairtab[(m | (m >> 12)) & 0xFFu];
+				acc.x += two.x; acc.y += two.y; acc.z += two.z; acc.w += two.w;
 			}
 		}
 		const uint32_t a[4] = {acc.x, acc.y, acc.z, acc.w};
@@ -774,7 +788,9 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	int q = 1;
 	if (BUSY) {
 		// v2: 10-bit DC + 2-bit end of block per block; v3: DC codes are at least 2 bits long
-		q = census_first_candidate(fc, ngroups, cpad, nmb, s.grows, s.lenlut, s.misc + 8, nblk * (V3 ? 4 : 12), limit_bits);
+		// (the pair table borrows the emit phase's staging area)
+		q = census_first_candidate(fc, ngroups, cpad, nmb, s.grows, s.lenlut, s.misc + 8, reinterpret_cast<uint4 *>(s.stage),
+		                           nblk * (V3 ? 4 : 12), limit_bits);
 		q = max(q, 2);   // q = 1 failed in the first kernel
 	}
 	uint32_t total_bits = 0;
@@ -932,7 +948,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 			if (nrows & 0x80) {
 				for (int half = 0; half < 2; half++) {
 					__syncwarp();
-					uint32_t live = stage_dense(gp, half, qs, stage, T);
+					uint32_t live = stage_dense<BUSY>(gp, half, qs, stage, T);
 					if (!act) live = 0;
 					nnz += __popc(live);
 					while (live) {
@@ -1010,7 +1026,8 @@ size_t bs_pack_smem_bytes(bool v3, bool smem_stream, const BsGeometry &geo, int 
 	take((size_t)ngroups);                // grows
 	take(2 * padded);                     // lens
 	if (v3) take(2 * padded);             // dcval
-	take(64 * (size_t)threads);           // stage: 16 words per thread
+	// stage: 16 words per thread; the census of the BUSY kernel borrows 4 KB of it for its pair table
+	take(64 * (size_t)threads > 4096 ? 64 * (size_t)threads : 4096);
 	return n;
 }
 
