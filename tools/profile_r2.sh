@@ -1,6 +1,6 @@
 # One gpurun call: tests, bench (both arms), launch list, ncu full captures of the hot kernels,
 # drop-in latencies. Outputs under gpurun_out/ with the prefix given as $1 (default r2).
-P=${1:-r2}
+P=${1:-r2b}
 set -x
 python -m pytest tests -m gpu -q 2>&1 | tail -5 > gpurun_out/${P}_tests.log
 python bench.py --steps 20 --warmup 5 > gpurun_out/${P}_bench.json 2> gpurun_out/${P}_bench.err
