@@ -273,6 +273,8 @@ class Ctx:
             self.host_group = dist.new_group(backend="gloo")
         self.stream = torch.cuda.current_stream()
         self.fdct = fdct_from_name(args.fdct)
+        self.fdct_name = args.fdct
+        self.sm_count = torch.cuda.get_device_properties(self.local).multi_processor_count
         self.peak, self.peak_src = load_peak()
 
     def barrier(self):
@@ -490,6 +492,18 @@ def bench_headline(ctx, line):
             per_kernel[name] = {"algorithmic_bytes_per_launch": algo * frames_per_launch, "launch_ms": ms, "gbs": gbs,
                                 "frac": gbs / ctx.peak, "traffic": traffic.get(name),
                                 "share_of_kernel_time": ms * pairs / (dct_ms + pack_ms) if dct_ms + pack_ms else None}
+        if ctx.fdct_name == "sse2" and clocks and clocks.get("sm_mhz"):
+            # What bounds the FDCT kernel is its own instruction mix (straight-line code: static = executed): 864 ALU-pipe
+            # instructions at 2 cycles and 745 IMAD at 2 + 64 IMAD.HI at 4 cycles per warp and sub-partition, the rates measured
+            # by tools/ubench/pipes.cu (profiles/r2_microopt_ab.txt); one warp = one group of 32 blocks.
+            warps = frames_per_launch * ((wl.width // 16) * (wl.height // 16) * 2 + 31) // 32 \
+                + frames_per_launch * ((wl.width // 16) * (wl.height // 16) * 4 + 31) // 32
+            cycles = max(864 * 2, 745 * 2 + 64 * 4)
+            bound_ms = warps / (4.0 * ctx.sm_count) * cycles / (clocks["sm_mhz"] * 1e3)
+            per_kernel["bs_dct_kernel"]["pipe_bound"] = {
+                "alu_cycles_per_warp": 864 * 2, "fma_cycles_per_warp": 745 * 2 + 64 * 4, "bound_ms": bound_ms,
+                "frac": bound_ms / per_kernel["bs_dct_kernel"]["launch_ms"] if per_kernel["bs_dct_kernel"]["launch_ms"] else None,
+                "source": "static SASS mix of bs_dct_kernel<sse2> x measured pipe issue rates (DESIGN.md 4.1)"}
         whole = wl.algo_bytes * n / (step_ms / 1000.0) / 1e9
         e2e_value = world * n * e2e_steps / (e2e_ms / 1000.0)
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * wl.frame_bytes,
@@ -523,7 +537,8 @@ def bench_headline(ctx, line):
                          "peak_source": ctx.peak_src, "algorithmic_bytes_per_launch": wl.algo_bytes * frames_per_launch,
                          "algorithmic_bytes_per_frame": wl.algo_bytes, "step_ms": step_ms,
                          "per_kernel": per_kernel, "kernel_ms_per_step_serial": (dct_ms + pack_ms) / 5, "step_ms_total": elapsed_ms,
-                         "note": "integer-issue bound kernels (ncu: profiles/r2_*): the HBM fraction is reported, not the limiter"},
+                         "note": "integer-pipe bound kernels (ncu: profiles/r2b_*; FDCT: per_kernel.bs_dct_kernel.pipe_bound): the HBM "
+                                 "fraction is reported, not the limiter"},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
