@@ -496,8 +496,8 @@ def bench_headline(ctx, line):
             # What bounds the FDCT kernel is its own instruction mix (straight-line code: static = executed): 864 ALU-pipe
             # instructions at 2 cycles and 745 IMAD at 2 + 64 IMAD.HI at 4 cycles per warp and sub-partition, the rates measured
             # by tools/ubench/pipes.cu (profiles/r2_microopt_ab.txt); one warp = one group of 32 blocks.
-            warps = frames_per_launch * ((wl.width // 16) * (wl.height // 16) * 2 + 31) // 32 \
-                + frames_per_launch * ((wl.width // 16) * (wl.height // 16) * 4 + 31) // 32
+            nmb = (wl.width // 16) * (wl.height // 16)
+            warps = frames_per_launch * ((2 * nmb + 31) // 32 + (4 * nmb + 31) // 32)
             cycles = max(864 * 2, 745 * 2 + 64 * 4)
             bound_ms = warps / (4.0 * ctx.sm_count) * cycles / (clocks["sm_mhz"] * 1e3)
             per_kernel["bs_dct_kernel"]["pipe_bound"] = {
