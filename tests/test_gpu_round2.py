@@ -70,6 +70,46 @@ def test_bs_large_budget_multi_chunk(restated):
     assert np.array_equal(got_out, exp_out)
 
 
+def test_bs_first_pass_total_exact_for_huge_levels(restated):
+    """The q = 1 pass has its own list walk (level = (y + 1) >> 1, rows of the length table clamped at
+    level 63): budgets exactly at, just below and just above the q = 1 stream size of a frame made of
+    DCT basis sign patterns (levels up to 462, escape codes) and of a noisy frame must leave q = 1
+    exactly where the oracle does."""
+    w, h = 64, 48
+    n = np.arange(8)
+    luma = np.zeros((h, w), np.uint8)
+    k = 0
+    for by in range(h // 8):
+        for bx in range(w // 8):
+            u, v = (3 * k + 1) % 8, (5 * k + 2) % 8
+            basis = np.outer(np.cos((2 * n + 1) * u * np.pi / 16), np.cos((2 * n + 1) * v * np.pi / 16))
+            luma[8 * by:8 * by + 8, 8 * bx:8 * bx + 8] = np.where((basis > 0) ^ (k & 1 == 1), 255, 0)
+            k += 1
+    chroma = np.tile(np.array([[0, 255], [255, 0]], np.uint8), (h // 4, w // 2))
+    extreme = np.concatenate([luma.ravel(), chroma.ravel()])
+    noisy = synth.gen_frame(5, w, h, 5)
+    for frame in (extreme, noisy):
+        lo, hi = 8, 200000
+        while lo < hi:   # smallest budget that admits q = 1
+            mid = (lo + hi) // 2
+            _, r = restated.bs_encode_batch(0, w, h, frame[None], mid, oracle.FDCT_SSE2, stride=200000)
+            if r[0, 2] <= 1:
+                hi = mid
+            else:
+                lo = mid + 1
+        sizes = np.array([lo - 4, lo - 2, lo - 1, lo, lo + 1, lo + 2, lo + 4], np.int32)
+        frames = np.repeat(frame[None], len(sizes), axis=0)
+        exp_out, exp_res = restated.bs_encode_batch(0, w, h, frames, sizes, oracle.FDCT_SSE2, stride=int(sizes.max()))
+        enc = pb.BsEncoder(pb.CODEC_V2, w, h, pb.FDCT_SSE2, max_batch=8)
+        got_out, got_res = enc.encode_host(frames, sizes, stride=int(sizes.max()))
+        enc.close()
+        assert exp_res[:, 2].min() == 1 and 1 < exp_res[:, 2].max() < 64
+        assert np.array_equal(got_res, exp_res)
+        for i, sz in enumerate(sizes):
+            assert np.array_equal(got_out[i, :sz], exp_out[i, :sz]), "budget %d" % sz
+
+
+
 @pytest.mark.parametrize("n", [5, 200], ids=["few-frames-640-threads", "many-frames-320-threads"])
 @pytest.mark.parametrize("codec", [0, 1], ids=["v2", "v3"])
 def test_bs_busy_content_skips_hopeless_scales(restated, n, codec):
