@@ -48,14 +48,16 @@ namespace psxb200 {
 __constant__ uint2 c_qmagic[64];
 // One zero guard byte, then [min(level,63)][run] -> code length in bits incl. sign (22 = escape),
 // 0 for level 0 (the list walks index it with run + 1, see price_entry); padded to whole words.
+// (Global, not constant memory: every CTA copies the tables to shared memory with one word per
+// thread, and constant-bank reads at 32 different addresses per warp are served one by one.)
 constexpr int LENLUT1_BYTES = 4 + 64 * 64;
-__constant__ uint8_t c_lenlut1[LENLUT1_BYTES];
+__device__ __align__(16) uint8_t g_lenlut1[LENLUT1_BYTES];
 // [min(level,41)][min(run,32)] -> (len << 24) | code with the sign bit (LSB) clear; level 0 -> 0;
 // escape (including all of row 41 and column 32) -> (22 << 24) with code 0. Copied to shared
 // memory by every CTA.
 __device__ uint32_t g_vlc[BS_VLC_ROWS * BS_VLC_COLS];
 // v3 DC delta codes: [0] chroma, [1] luma.
-__constant__ uint32_t c_dcvlc[2 * 512];
+__device__ uint32_t g_dcvlc[2 * 512];
 
 __host__ __device__ constexpr int zigzag_at(int i) {
 	constexpr int t[64] = {BS_ZIGZAG_LIST};
@@ -121,9 +123,9 @@ cudaError_t bs_upload_tables() {
 	// once per device, before any kernel of this library has been launched on it.
 	if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
 	if ((e = cudaMemcpyToSymbol(c_qmagic, qmagic, sizeof(qmagic))) != cudaSuccess) return e;
-	if ((e = cudaMemcpyToSymbol(c_lenlut1, lenlut1, sizeof(lenlut1))) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(g_lenlut1, lenlut1, sizeof(lenlut1))) != cudaSuccess) return e;
 	if ((e = cudaMemcpyToSymbol(g_vlc, vlc, sizeof(vlc))) != cudaSuccess) return e;
-	if ((e = cudaMemcpyToSymbol(c_dcvlc, dcvlc, sizeof(dcvlc))) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(g_dcvlc, dcvlc, sizeof(dcvlc))) != cudaSuccess) return e;
 	if ((e = cudaMemcpyToSymbol(g_edc, edc, sizeof(edc))) != cudaSuccess) return e;
 	if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
 	g_tables_uploaded[dev] = true;
@@ -753,9 +755,9 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	const int words = max_size > 0 ? (max_size + 3) / 4 + 2 : 0;
 
 	for (int i = tid; i < LENLUT1_BYTES / 4; i += T)
-		reinterpret_cast<uint32_t *>(s.lenlut - 1)[i] = reinterpret_cast<const uint32_t *>(c_lenlut1)[i];
+		reinterpret_cast<uint32_t *>(s.lenlut - 1)[i] = reinterpret_cast<const uint32_t *>(g_lenlut1)[i];
 	for (int i = tid; i < BS_VLC_ROWS * BS_VLC_COLS; i += T) s.vlc[i] = g_vlc[i];
-	if (V3) for (int i = tid; i < 1024; i += T) s.dctab[i] = c_dcvlc[i];
+	if (V3) for (int i = tid; i < 1024; i += T) s.dctab[i] = g_dcvlc[i];
 	for (int i = tid; i < words; i += T) stream[i] = 0;
 	if (tid < 8) s.misc[tid] = 0;
 	for (int b = nblk + tid; b < padded; b += T) s.lens[b] = 0;   // scan padding
