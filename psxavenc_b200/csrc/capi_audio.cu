@@ -142,6 +142,7 @@ int psxb200::spu_encode_host_subset(int n_streams, int first, int step, const in
 		const long run_chains = std::max(1024L, (4L << 20) / chain_bytes);
 		const int run_groups = (int)std::max(1L, (run_chains + pitch - 1) / pitch);
 		if (n_groups >= 2 * run_groups) {
+			static_assert(SPU_PIPE_STREAMS == 4, "one StreamDrain per extra stream below");
 			StreamDrain drains[SPU_PIPE_STREAMS - 1] = {StreamDrain(ctx->pipe[1]), StreamDrain(ctx->pipe[2]), StreamDrain(ctx->pipe[3])};
 			int k = 0;
 			for (int g0 = 0; g0 < n_groups; g0 += run_groups, k++) {
