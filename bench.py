@@ -977,7 +977,7 @@ def bench_spu_sine(ctx):
     gpu_dt, gpu_out = drive(pb.lib(), gpu_blocks)
     out = {"workload": "spu: mono 22050 Hz 440 Hz sine, %d s, one <=28-sample block per psx_audio_spu_encode call" % seconds,
            "dropin_gpu": {"value": gpu_blocks * 28 / gpu_dt / 1e6, "unit": "Msamples/s", "us_per_call": gpu_dt / gpu_blocks * 1e6,
-                          "blocks": gpu_blocks, "api": "psx_audio_spu_encode (drop-in symbol, zero-copy staging)"}}
+                          "blocks": gpu_blocks, "api": "psx_audio_spu_encode (drop-in symbol; samples in the kernel parameters, results and completion flag in mapped host memory)"}}
     if hasattr(backend, "lib") and backend.kind == "reference":
         cpu_dt, cpu_out = drive(backend.lib, blocks)
         if not np.array_equal(cpu_out[:gpu_blocks], gpu_out):

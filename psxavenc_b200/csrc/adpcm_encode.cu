@@ -26,12 +26,6 @@ namespace psxb200 {
 
 constexpr int UNIT = 28;
 
-struct ChannelState {   // psx_audio_encoder_channel_state_t (libpsxav.h:53-57)
-	int qerr;
-	int pad_;
-	unsigned long long mse;
-	int prev1, prev2;
-};
 static_assert(sizeof(ChannelState) == 24, "state layout");
 
 __device__ __forceinline__ int filter_k1(int f) { return f == 0 ? 0 : f == 1 ? 60 : f == 2 ? 115 : f == 3 ? 98 : 122; }
@@ -204,6 +198,54 @@ adpcm_spu_kernel(int n_streams, int stream_first, int stream_step, const int16_t
 		st.prev1 = p1; st.prev2 = p2; st.mse = mse;
 		states[stream] = st;
 	}
+}
+
+// One short chain whose samples and state travel in the kernel's parameters and whose blocks,
+// state and completion flag go to page-locked host memory mapped into the device address space:
+// the drop-in psx_audio_spu_encode is called with one 28-sample block at a time by the
+// reference's own encode_file_spu (filefmt.c:243), so what counts there is the latency of a
+// call — no read over the link, no copy engine, and the host sees the flag as soon as the
+// results have landed instead of waiting for the stream.
+__global__ void __launch_bounds__(32)
+adpcm_spu_small_kernel(const __grid_constant__ SpuSmallCall call) {
+	const int lane = threadIdx.x & 31, sub = lane & 15;
+	const bool live = lane < 16;   // one chain: the second half-warp only keeps the shuffles of encode_unit company
+	const int units = (call.count + UNIT - 1) / UNIT;
+	int p1 = call.state.prev1, p2 = call.state.prev2;
+	unsigned long long mse = call.state.mse;
+	for (int u = 0; u < units; u++) {
+		int s[UNIT];
+#pragma unroll
+		for (int i = 0; i < UNIT; i++) s[i] = u * UNIT + i < call.count ? (int)call.samples[u * UNIT + i] : 0;
+		uint32_t codes[4];
+		unsigned long long m;
+		int header;
+		bool mine;
+		int n1 = p1, n2 = p2;
+		encode_unit<5, 12>(s, call.state.qerr, n1, n2, sub, codes, m, header, mine);
+		p1 = n1; p2 = n2; mse = m;
+		if (live && mine) {
+			uint4 blk;   // header, flags = 0, 14 bytes of nibble pairs, low nibble first (adpcm.c:367-372)
+			blk.x = (uint32_t)header | (codes[0] << 16);
+			blk.y = (codes[0] >> 16) | (codes[1] << 16);
+			blk.z = (codes[1] >> 16) | (codes[2] << 16);
+			blk.w = (codes[2] >> 16) | (codes[3] << 16);
+			*reinterpret_cast<uint4 *>(call.out + 16 * u) = blk;
+		}
+	}
+	if (lane == 0) {
+		ChannelState st = call.state;
+		if (units > 0) { st.prev1 = p1; st.prev2 = p2; st.mse = mse; }
+		*call.state_out = st;
+	}
+	__threadfence_system();   // every lane's stores are out before the flag
+	__syncwarp();
+	if (lane == 0) *call.flag = call.seq;
+}
+
+cudaError_t adpcm_launch_spu_small(const SpuSmallCall &call, cudaStream_t stream) {
+	adpcm_spu_small_kernel<<<1, 32, 0, stream>>>(call);
+	return cudaGetLastError();
 }
 
 // ---- XA ----------------------------------------------------------------------------------

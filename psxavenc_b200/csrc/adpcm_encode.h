@@ -8,10 +8,33 @@ namespace psxb200 {
 
 constexpr int ADPCM_THREADS = 128;
 
+struct ChannelState {   // psx_audio_encoder_channel_state_t (libpsxav.h:53-57)
+	int qerr;
+	int pad_;
+	unsigned long long mse;
+	int prev1, prev2;
+};
+
+// A short SPU chain handed over in the kernel's parameters (adpcm_launch_spu_small)
+constexpr int SPU_SMALL_SAMPLES = 4 * 28;
+struct SpuSmallCall {
+	int16_t samples[SPU_SMALL_SAMPLES];   // the chain's samples, gathered (pitch 1)
+	ChannelState state;                   // incoming state
+	int count;                            // samples, <= SPU_SMALL_SAMPLES
+	uint32_t seq;                         // value written to *flag when everything else has been written
+	// device addresses of mapped host memory:
+	uint8_t *out;                         // 16 bytes per 28 samples
+	ChannelState *state_out;              // outgoing state
+	volatile uint32_t *flag;              // completion flag
+};
+
 // The launch's i-th chain (i < n_streams) is stream stream_first + i * stream_step of the arrays.
 cudaError_t adpcm_launch_spu(int n_streams, const int16_t *d_samples, int pitch, long group_stride, int sample_count,
                              const int *d_counts, void *d_states, uint8_t *d_out, long out_stride, cudaStream_t stream,
                              int stream_first = 0, int stream_step = 1);
+
+// One chain of at most SPU_SMALL_SAMPLES samples: one launch of one warp, nothing read from memory.
+cudaError_t adpcm_launch_spu_small(const SpuSmallCall &call, cudaStream_t stream);
 
 // int16 elements of a stream's input that the reference reads (and so must be readable)
 long adpcm_xa_input_extent(int stereo, int bits_per_sample, int sample_count);

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 
@@ -36,6 +38,8 @@ struct AudioContext {
 	DeviceBuffer<uint8_t> out;
 	DeviceBuffer<uint8_t> states;
 	PinnedBuffer<uint8_t> stage;   // zero-copy staging: samples | states | blocks
+	PinnedBuffer<uint8_t> small;   // results of the parameter-borne small SPU calls: blocks | state | flag
+	uint32_t seq = 0;              // completion-flag value of the last small call
 	const uint32_t *edc = nullptr;
 	int ensure() {
 		if (!stream) CU_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -95,6 +99,42 @@ int psxb200::spu_encode_host_subset(int n_streams, int first, int step, const in
 	StreamDrain drain(st);
 	const long block_bytes = 16L * ((sample_count + 27) / 28);
 	const int n_sub = (n_streams - first + step - 1) / step;
+
+	if (n_streams == 1 && sample_count <= SPU_SMALL_SAMPLES) {
+		// one block or a few (the reference's own encode_file_spu hands over 28 samples per call,
+		// filefmt.c:243): samples and state ride in the kernel's parameters, the kernel writes blocks,
+		// state and a completion flag into mapped host memory, and the call returns when the flag
+		// shows — one launch, no copies, no stream synchronisation
+		constexpr size_t OUT = 0, STATE = 64, FLAG = 96, BYTES = 128;
+		if (!ctx->small.ptr) {
+			CU_TRY(ctx->small.reserve(BYTES));
+			memset(ctx->small.ptr, 0, BYTES);
+		}
+		uint8_t *d_base = ctx->small.device_ptr();
+		if (!d_base) return fail("psxb200_spu_encode_host: mapped staging unavailable");
+		SpuSmallCall call;
+		for (int i = 0; i < sample_count; i++) call.samples[i] = h_samples[(long)i * pitch];
+		memcpy(&call.state, h_states, STATE_BYTES);
+		call.count = sample_count;
+		if (++ctx->seq == 0) ctx->seq = 1;
+		call.seq = ctx->seq;
+		call.out = d_base + OUT;
+		call.state_out = reinterpret_cast<ChannelState *>(d_base + STATE);
+		call.flag = reinterpret_cast<volatile uint32_t *>(d_base + FLAG);
+		CU_TRY(adpcm_launch_spu_small(call, st));
+		g_launches += 1;
+		const volatile uint32_t *flag = reinterpret_cast<const volatile uint32_t *>(ctx->small.ptr + FLAG);
+		const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(20);
+		bool seen = false;
+		for (unsigned spins = 0; !(seen = *flag == call.seq); spins++)
+			if ((spins & 0xFFF) == 0xFFF && std::chrono::steady_clock::now() > deadline) break;
+		if (!seen) CU_TRY(cudaStreamSynchronize(st));   // a failed launch or a wedged device surfaces here
+		std::atomic_thread_fence(std::memory_order_acquire);
+		drain.armed = false;
+		memcpy(h_out, ctx->small.ptr + OUT, (size_t)block_bytes);
+		memcpy(h_states, ctx->small.ptr + STATE, STATE_BYTES);
+		return 0;
+	}
 
 	if (n_streams == 1 && (size_t)sample_count * 2 <= ZERO_COPY_BYTES) {
 		// one short chain (the drop-in's usual call): gather its samples into the mapped staging
