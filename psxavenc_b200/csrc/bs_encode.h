@@ -20,7 +20,10 @@ constexpr int BS_DCT_THREADS = BS_DCT_THREADS_PER_CTA;
 #ifndef BS_DCT_MIN_CTAS
 #define BS_DCT_MIN_CTAS 9
 #endif
-constexpr int BS_PACK_MAX_THREADS = 640;
+#ifndef BS_PACK_MAX_THREADS_PER_CTA
+#define BS_PACK_MAX_THREADS_PER_CTA 640
+#endif
+constexpr int BS_PACK_MAX_THREADS = BS_PACK_MAX_THREADS_PER_CTA;
 // per block in the coefficient plane: up to 8 uint4 rows of list entries ((y << 6) | zig-zag
 // position, 16 bits each, highest position first, zero padded; only the rows the group's longest
 // list needs are written) + 1 meta uint4: sign mask lo/hi, |DC| | list length << 16, longest list
