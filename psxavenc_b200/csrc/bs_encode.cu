@@ -31,6 +31,7 @@
 // one has the same divisor for all 63 AC coefficients of a pass, and a coefficient is nonzero at
 // q iff y >= q. For 8-bit input |c| <= 8192 and quant >= 16, so y < 1024 (10 bits).
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 
 #include <mutex>
@@ -707,7 +708,16 @@ __device__ __forceinline__ StrFrame str_frame(const BsStrLayout &str, int f) {
 // takes only the marked frames, rules out the hopeless quant scales with the census and then
 // carries on with the first-fit search. (Two kernels rather than one branch: the extra code in the
 // common kernel cost it a third of its speed, measured.)
-template <bool V3, bool SMEM_STREAM, bool STR, bool BUSY, int MAX_THREADS, int MIN_CTAS>
+//
+// CL > 1: a thread-block CLUSTER of CL CTAs (one per SM) shares a frame — for calls with only a
+// few frames (the drop-in symbols encode one at a time), where the latency of a frame is what
+// counts and a single SM needs 31 us for its ~100 k warp instructions. The CTAs of the cluster
+// split the plane groups between them in the search and in the emit phase; every CTA keeps the
+// whole frame's block lengths (each length is stored into all CL shared memories through
+// distributed shared memory) and its own image of the bitstream holding only its blocks' codes;
+// pass totals and the coefficient count are summed over the cluster after a cluster barrier,
+// and the copy-out ORs the CL images together, each CTA writing a share of the words.
+template <bool V3, bool SMEM_STREAM, bool STR, bool BUSY, int MAX_THREADS, int MIN_CTAS, int CL = 1>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS)
 bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk, int ngroups, int nsgroups, int cpad,
                int nmb, int codec,
@@ -716,7 +726,10 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
                const BsStrLayout str) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
-	const int f = blockIdx.x;
+	static_assert(CL == 1 || (SMEM_STREAM && !BUSY), "cluster mode: shared-memory image, common kernel only");
+	namespace cg = cooperative_groups;
+	const int f = CL > 1 ? (int)blockIdx.x / CL : (int)blockIdx.x;
+	const int rank = CL > 1 ? (int)cg::this_cluster().block_rank() : 0;   // == blockIdx.x % CL
 	if (BUSY && results[f].quant_scale != 0) return;   // finished by the first kernel
 	const int padded = nsgroups * 32;   // blocks in bitstream order, rounded up to whole scan groups
 	const int stream_words = (max_size_bound + 3) / 4 + 2;
@@ -776,6 +789,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		}
 	}
 	__syncthreads();
+	if (CL > 1) cg::this_cluster().sync();   // every CTA of the cluster runs and has its tables before any remote store
 	if (V3) dc_delta_codes(codec, nmb, s.dcval, reinterpret_cast<int *>(s.misc + 8));
 	// code of block b's DC delta (chroma table for Cr/Cb, luma for Y1..Y4)
 	auto dc_code = [&](int b) { return s.dctab[((b % 6) < 2 ? 0 : 512) + (s.dcval[b] & 0x1FF)]; };
@@ -786,7 +800,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	// point too, mdec.c:323-325) and is abandoned early.
 	const int limit_bits = max_size >= 8 ? 16 * ((max_size - 8) >> 1) - 10 : -1;
 	// frames with a tiny budget are not worth a second kernel
-	const bool census_possible = SMEM_STREAM && max_size >= 2016;
+	const bool census_possible = CL == 1 && SMEM_STREAM && max_size >= 2016;   // (a cluster finishes its frame itself)
 	int q = 1;
 	if (BUSY) {
 		// v2: 10-bit DC + 2-bit end of block per block; v3: DC codes are at least 2 bits long
@@ -802,7 +816,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		// from a shared ticket counter instead of this static round-robin measured no better
 		uint32_t *total = &s.misc[q % 3];
 		int visited = 0;
-		for (int g = ngroups - 1 - wid; g >= 0; g -= nw) {
+		for (int g = ngroups - 1 - (wid * CL + rank); g >= 0; g -= nw * CL) {
 			const int b = bs_plane_to_block(g * 32 + lane, cpad, nmb);
 			int bits = 0;
 			if (b >= 0) {
@@ -812,7 +826,12 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 				if (!BUSY && q == 1 && !(rows & 0x80)) bits = ac_bits_q1(gp, rows, s.lut1);
 				else bits = (rows & 0x80) ? ac_bits_dense(gp, qs, s.lenlut) : ac_bits(gp, rows, qs, s.lut1);
 				bits += 2 + (V3 ? (int)(dc_code(b) >> 24) : 10);
-				s.lens[b] = (uint16_t)bits;
+				if (CL > 1) {
+#pragma unroll
+					for (int r = 0; r < CL; r++) cg::this_cluster().map_shared_rank(s.lens, r)[b] = (uint16_t)bits;
+				} else {
+					s.lens[b] = (uint16_t)bits;
+				}
 			}
 			visited++;
 			const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)bits);
@@ -823,7 +842,15 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		}
 		if (!BUSY && q == 1 && lane == 0) atomicAdd(&s.misc[4], (uint32_t)visited);
 		__syncthreads();
-		total_bits = *total;
+		if (CL > 1) {
+			// the pass is over in every CTA (and all remote length stores have landed): sum the totals
+			cg::this_cluster().sync();
+			total_bits = 0;
+#pragma unroll
+			for (int r = 0; r < CL; r++) total_bits += *cg::this_cluster().map_shared_rank(total, r);
+		} else {
+			total_bits = *total;
+		}
 		if (tid == 0) s.misc[(q + 2) % 3] = 0;
 		// stream = blocks + 10-bit end-of-frame code; byte budget rule of flush_bits
 		int units = (int)((total_bits + 10 + 15) >> 4);
@@ -865,6 +892,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		}
 	};
 	if (q >= 64) {
+		if (CL > 1 && rank != 0) return;   // (nobody reads a peer's shared memory on this path)
 		for (int i = tid; i < (max_size >> 2); i += T) *word_at(i) = 0;
 		if (!STR)
 			for (int i = (max_size & ~3) + tid; i < max_size; i += T) out[(size_t)f * out_stride + i] = 0;
@@ -910,7 +938,7 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		const QuantScale qs(q);
 		uint32_t *stage = s.stage + tid;
 		uint32_t nnz = 0;
-		for (int g = ngroups - 1 - wid; g >= 0; g -= nw) {
+		for (int g = ngroups - 1 - (wid * CL + rank); g >= 0; g -= nw * CL) {
 			// Lanes walk different numbers of coefficients, so the warp is brought back together
 			// (__syncwarp) before every convergent stretch — left to itself it ran the staging code
 			// below in up to seven separate lane groups per group of blocks (ncu: executed 395
@@ -989,27 +1017,45 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	__syncthreads();
 
 	// ---- (4) header, results, copy-out -----------------------------------------------------
+	uint32_t coefficients = s.misc[3];
+	// word i of the bitstream image: in a cluster the OR of the CTAs' images
+	auto image_word = [&](int i) -> uint32_t {
+		if (CL == 1) return stream[i];
+		uint32_t x = 0;
+#pragma unroll
+		for (int r = 0; r < CL; r++) x |= cg::this_cluster().map_shared_rank(s.stream, r)[i];
+		return x;
+	};
+	if (CL > 1) {
+		cg::this_cluster().sync();   // every CTA's image and coefficient count are complete
+		coefficients = 0;
+#pragma unroll
+		for (int r = 0; r < CL; r++) coefficients += cg::this_cluster().map_shared_rank(s.misc, r)[3];
+	}
 	int units = (int)((total_bits + 10 + 15) >> 4);
-	int hwords = ((int)s.misc[3] + 2 * nblk + 2 + 0x3F) & ~0x3F;   // mdec.c:497,507,719,726
+	int hwords = ((int)coefficients + 2 * nblk + 2 + 0x3F) & ~0x3F;   // mdec.c:497,507,719,726
 	int blocks_used = (hwords + 1) >> 1;
-	if (tid == 0)
+	if (tid == 0 && rank == 0)
 		results[f] = psxb200_bs_result_t{(8 + 2 * units + 3) & ~3, blocks_used, q, hwords};
 	uint32_t hdr0 = (uint32_t)(blocks_used & 0xFFFF) | 0x38000000u;
 	uint32_t hdr1 = (uint32_t)q | ((V3 ? 3u : 2u) << 16);
-	for (int i = tid; i < (max_size >> 2); i += T) {
+	// (a cluster's CTAs take contiguous shares of the words)
+	const int nwords = max_size >> 2, share = (nwords + CL - 1) / CL;
+	for (int i = rank * share + tid; i < min(nwords, (rank + 1) * share); i += T) {
 		uint32_t v;
 		if (i == 0) v = hdr0;
 		else if (i == 1) v = hdr1;
-		else { uint32_t x = stream[i - 2]; v = (x >> 16) | (x << 16); }
+		else { uint32_t x = image_word(i - 2); v = (x >> 16) | (x << 16); }
 		*word_at(i) = v;
 	}
-	if (STR) write_str_headers((uint32_t)((8 + 2 * units + 3) & ~3), hdr0, hdr1);
-	if (!STR && tid < (max_size & 3)) {
+	if (STR && rank == 0) write_str_headers((uint32_t)((8 + 2 * units + 3) & ~3), hdr0, hdr1);
+	if (!STR && rank == 0 && tid < (max_size & 3)) {
 		int i = (max_size & ~3) + tid;   // >= 8 here, since the frame fitted
-		uint32_t x = stream[(i >> 2) - 2];
+		uint32_t x = image_word((i >> 2) - 2);
 		uint32_t v = (x >> 16) | (x << 16);
 		out[(size_t)f * out_stride + i] = (uint8_t)(v >> (8 * (i & 3)));
 	}
+	if (CL > 1) cg::this_cluster().sync();   // nobody leaves while a peer still reads its image
 }
 
 // ---- launchers ---------------------------------------------------------------------------
@@ -1083,6 +1129,55 @@ static cudaError_t launch_pack_t(int threads, size_t smem, int n, const uint4 *d
 	                                   d_max_sizes, max_size_bound, d_out, out_stride, d_results, d_gstream,
 	                                   gstream_stride, str);
 	return cudaGetLastError();
+}
+
+// Cluster mode (see bs_pack_kernel): n * BS_PACK_CLUSTER CTAs, BS_PACK_CLUSTER of them per frame.
+template <bool V3, bool STR>
+static cudaError_t launch_pack_cluster_t(int threads, size_t smem, int n, const uint4 *d_coefs, const BsGeometry &geo, int codec,
+                                         const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
+                                         psxb200_bs_result_t *d_results, const BsStrLayout &str, cudaStream_t stream) {
+	auto kern = bs_pack_kernel<V3, true, STR, false, BS_PACK_MAX_THREADS, 1, BS_PACK_CLUSTER>;
+	static bool configured[MAX_DEVICES];
+	{
+		int dev = 0;
+		cudaError_t e = cudaGetDevice(&dev);
+		if (e != cudaSuccess) return e;
+		if (dev < 0 || dev >= MAX_DEVICES) return cudaErrorInvalidDevice;
+		std::lock_guard<std::mutex> guard(g_device_lock);
+		if (!configured[dev]) {
+			int optin = 0;
+			e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+			if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+			if (e != cudaSuccess) return e;
+			configured[dev] = true;
+		}
+	}
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)n * BS_PACK_CLUSTER);
+	cfg.blockDim = dim3((unsigned)threads);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = BS_PACK_CLUSTER;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	uint32_t *no_gstream = nullptr;
+	return cudaLaunchKernelEx(&cfg, kern, d_coefs, geo.frame_stride_u4, geo.nblk, geo.ngroups, geo.nsgroups, geo.cgroups * 32,
+	                          geo.nmb, codec, d_max_sizes, max_size_bound, d_out, out_stride, d_results, no_gstream, (size_t)0, str);
+}
+
+cudaError_t bs_launch_pack_cluster(int codec, int threads, int n, const uint4 *d_coefs, const BsGeometry &geo,
+                                   const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
+                                   psxb200_bs_result_t *d_results, const BsStrLayout &str, cudaStream_t stream) {
+	const bool v3 = codec != 0;
+	const size_t smem = bs_pack_smem_bytes(v3, true, geo, max_size_bound, threads);
+#define PSXB200_CL_ARGS threads, smem, n, d_coefs, geo, codec, d_max_sizes, max_size_bound, d_out, out_stride, d_results, str, stream
+	if (str.sector_size) return v3 ? launch_pack_cluster_t<true, true>(PSXB200_CL_ARGS) : launch_pack_cluster_t<false, true>(PSXB200_CL_ARGS);
+	return v3 ? launch_pack_cluster_t<true, false>(PSXB200_CL_ARGS) : launch_pack_cluster_t<false, false>(PSXB200_CL_ARGS);
+#undef PSXB200_CL_ARGS
 }
 
 template <bool BUSY, int MAX_THREADS, int MIN_CTAS>

@@ -124,6 +124,16 @@ cudaError_t bs_launch_pack(int codec, int threads, int min_ctas, int n, const ui
                            psxb200_bs_result_t *d_results, uint32_t *d_gstream, size_t gstream_stride,
                            const BsStrLayout &str, cudaStream_t stream);
 
+// The same for calls with a few frames only: a cluster of BS_PACK_CLUSTER CTAs per frame (shared-memory image,
+// no second kernel: a cluster finishes its frame itself). `threads` per CTA, at most BS_PACK_MAX_THREADS.
+#ifndef BS_PACK_CLUSTER_CTAS
+#define BS_PACK_CLUSTER_CTAS 4
+#endif
+constexpr int BS_PACK_CLUSTER = BS_PACK_CLUSTER_CTAS;
+cudaError_t bs_launch_pack_cluster(int codec, int threads, int n, const uint4 *d_coefs, const BsGeometry &geo,
+                                   const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
+                                   psxb200_bs_result_t *d_results, const BsStrLayout &str, cudaStream_t stream);
+
 // STR mode, framing: sync/header/subheader of the video sectors and their FORM1 EDC
 // (filefmt.c:73-92, cdrom.c:55-74, 92-100), after bs_launch_pack wrote headers and payloads.
 cudaError_t bs_launch_str_framing(int n, int max_chunks, uint8_t *d_out, const BsStrLayout &str, cudaStream_t stream);

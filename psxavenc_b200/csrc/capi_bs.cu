@@ -192,6 +192,18 @@ static int bs_encode_chunked(psxb200_bs_encoder *enc, DeviceBuffer<uint4> &coefs
 		threads = 32 * std::max(1, std::min(BS_PACK_MAX_THREADS / 32, enc->geo.ngroups));
 		min_ctas = 1;
 	}
+	// Very few frames (the drop-in symbols): a cluster of CTAs per frame, see bs_pack_kernel
+	static const bool cluster_off = getenv("PSXB200_NO_CLUSTER") != nullptr;
+	int cluster = 1;
+	// (clusters are placed within a GPC, so they do not tile all SMs: with half of the SMs asked for, every cluster of
+	// the launch is resident at once — 37 clusters of 4 on 148 SMs ran in two waves, 36.9 us against 32.8 us without)
+	if (2 * n * BS_PACK_CLUSTER <= enc->sm_count && !enc->pack_threads_forced && !cluster_off) {
+		const int cl_threads = 32 * std::max(1, std::min(BS_PACK_MAX_THREADS / 32, (enc->geo.ngroups + BS_PACK_CLUSTER - 1) / BS_PACK_CLUSTER));
+		if (bs_pack_smem_bytes(enc->codec != 0, true, enc->geo, max_size_bound, cl_threads) <= BS_SMEM_BUDGET) {
+			cluster = BS_PACK_CLUSTER;
+			threads = cl_threads;
+		}
+	}
 	const size_t smem = bs_pack_smem_bytes(enc->codec != 0, true, enc->geo, max_size_bound, threads);
 	if (smem > BS_SMEM_BUDGET) {
 		gstride = (size_t)(max_size_bound + 3) / 4 + 2;
@@ -215,12 +227,18 @@ static int bs_encode_chunked(psxb200_bs_encoder *enc, DeviceBuffer<uint4> &coefs
 			str = *str_batch;
 			str.frame_base += first;   // the kernel positions every frame absolutely within the batch
 		}
-		CU_TRY(bs_launch_pack(enc->codec, threads, min_ctas, m, coefs.ptr, enc->geo,
-		                      (str_batch || !d_max_sizes) ? nullptr : d_max_sizes + first, max_size_bound,
-		                      str_batch ? d_out : d_out + (size_t)first * out_stride, out_stride, d_results + first, gstream,
-		                      gstride, str, stream));
+		if (cluster > 1)
+			CU_TRY(bs_launch_pack_cluster(enc->codec, threads, m, coefs.ptr, enc->geo,
+			                              (str_batch || !d_max_sizes) ? nullptr : d_max_sizes + first, max_size_bound,
+			                              str_batch ? d_out : d_out + (size_t)first * out_stride, out_stride, d_results + first,
+			                              str, stream));
+		else
+			CU_TRY(bs_launch_pack(enc->codec, threads, min_ctas, m, coefs.ptr, enc->geo,
+			                      (str_batch || !d_max_sizes) ? nullptr : d_max_sizes + first, max_size_bound,
+			                      str_batch ? d_out : d_out + (size_t)first * out_stride, out_stride, d_results + first, gstream,
+			                      gstride, str, stream));
 		if (enc->timing) CU_TRY(enc->mark(stream));
-		g_launches += gstream ? 2 : 3;   // FDCT, pack, and (shared-memory image) the pack kernel for deferred frames
+		g_launches += (gstream || cluster > 1) ? 2 : 3;   // FDCT, pack, and (shared-memory image) the pack kernel for deferred frames
 		if (str_batch && str.framing && str.format != FORMAT_STRV) {
 			CU_TRY(bs_launch_str_framing(m, max_size_bound / 2016, d_out, str, stream));
 			g_launches += 1;

@@ -70,6 +70,31 @@ def test_bs_large_budget_multi_chunk(restated):
     assert np.array_equal(got_out, exp_out)
 
 
+@pytest.mark.parametrize("codec", [pb.CODEC_V2, pb.CODEC_V3], ids=["v2", "v3"])
+def test_bs_cluster_mode_matches_single_cta_mode(restated, codec):
+    """Calls with very few frames run the pack kernel as a thread-block cluster per frame (the CTAs split
+    the plane groups, exchange block lengths and totals through distributed shared memory and OR their
+    bitstream images together); the same frames inside a larger call take the one-CTA-per-frame kernels.
+    Both must give the oracle's bytes — easy, typical and busy content (the cluster finishes busy frames
+    itself, without the census kernel), ragged budgets."""
+    w, h = 320, 240
+    few = np.stack([synth.gen_frame(i, w, h, nb) for i, nb in enumerate((0, 3, 6, 3, 5, 6))])
+    sizes_few = np.array([20160, 20160, 20160, 16128, 18144, 12096], np.int32)
+    filler = synth.gen_frames(100, 34, w, h, 3)
+    many = np.concatenate([few, filler])
+    sizes_many = np.concatenate([sizes_few, np.full(len(filler), 20160, np.int32)])
+    enc = pb.BsEncoder(codec, w, h, pb.FDCT_SSE2, max_batch=64)
+    out_few, res_few = enc.encode_host(few, sizes_few, stride=20160)          # 6 frames: cluster mode
+    out_many, res_many = enc.encode_host(many, sizes_many, stride=20160)      # 40 frames: one CTA per frame
+    enc.close()
+    exp_out, exp_res = restated.bs_encode_batch(codec, w, h, few, sizes_few, oracle.FDCT_SSE2, stride=20160)
+    assert len(set(exp_res[:, 2])) >= 3 and exp_res[:, 2].max() >= 8
+    assert np.array_equal(res_few, exp_res) and np.array_equal(res_many[:len(few)], exp_res)
+    for i, sz in enumerate(sizes_few):
+        assert np.array_equal(out_few[i, :sz], exp_out[i, :sz]), "cluster mode, frame %d" % i
+        assert np.array_equal(out_many[i, :sz], exp_out[i, :sz]), "single-CTA mode, frame %d" % i
+
+
 def test_bs_first_pass_total_exact_for_huge_levels(restated):
     """The q = 1 pass has its own list walk (level = (y + 1) >> 1, rows of the length table clamped at
     level 63): budgets exactly at, just below and just above the q = 1 stream size of a frame made of
