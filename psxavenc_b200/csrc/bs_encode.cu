@@ -34,6 +34,7 @@
 #include <cooperative_groups.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "bs_encode.h"
@@ -154,6 +155,10 @@ bs_dct_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, int n_fram
 	// tail of every list reads as "no coefficient" (masking the tail on read-back instead, without
 	// this block-wide zeroing and its barrier, measured 3 % slower).
 	__shared__ __align__(16) uint16_t s_list[64 * BS_DCT_THREADS];
+	// A pack kernel launched behind this one with programmatic stream serialisation (cluster mode
+	// with PSXB200_PDL=1) may start its set-up now; it waits for this grid's completion before it
+	// touches the plane. Without such a launch behind it this does nothing.
+	asm volatile("griddepcontrol.launch_dependents;");
 #pragma unroll
 	for (int j = 0; j < (64 * 2) / 16; j++)
 		reinterpret_cast<uint4 *>(s_list)[threadIdx.x + BS_DCT_THREADS * j] = make_uint4(0, 0, 0, 0);
@@ -774,6 +779,10 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 	for (int i = tid; i < words; i += T) stream[i] = 0;
 	if (tid < 8) s.misc[tid] = 0;
 	for (int b = nblk + tid; b < padded; b += T) s.lens[b] = 0;   // scan padding
+	// cluster mode may be launched with programmatic stream serialisation (PSXB200_PDL=1): everything
+	// up to here then ran beside the FDCT kernel, and the plane may only be read once that grid has
+	// completed (a no-op otherwise)
+	if (CL > 1) asm volatile("griddepcontrol.wait;" ::: "memory");
 	for (int g = tid; g < ngroups; g += T) {
 		// every lane's meta row carries the group's longest list and the dense flag
 		uint32_t longest = reinterpret_cast<const uint32_t *>(fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + BS_META_ROW * 32)[3];
@@ -789,7 +798,16 @@ bs_pack_kernel(const uint4 *__restrict__ coefs, size_t frame_stride_u4, int nblk
 		}
 	}
 	__syncthreads();
-	if (CL > 1) cg::this_cluster().sync();   // every CTA of the cluster runs and has its tables before any remote store
+	if (CL > 1) {
+		// latency mode: pull the rows of this warp's groups towards L1 now — the walks below fetch a
+		// group's rows one after the other, each a round trip to L2 otherwise
+		for (int g = ngroups - 1 - (wid * CL + rank); g >= 0; g -= nw * CL) {
+			const int rows = s.grows[g];
+			const uint4 *gp = fc + (size_t)g * (BS_U4_PER_BLOCK * 32) + lane;
+			for (int r = 0; r < ((rows & 0x80) ? 8 : rows); r++) asm volatile("prefetch.global.L1 [%0];" ::"l"(gp + r * 32));
+		}
+		cg::this_cluster().sync();   // every CTA of the cluster runs and has its tables before any remote store
+	}
 	if (V3) dc_delta_codes(codec, nmb, s.dcval, reinterpret_cast<int *>(s.misc + 8));
 	// code of block b's DC delta (chroma table for Cr/Cb, luma for Y1..Y4)
 	auto dc_code = [&](int b) { return s.dctab[((b % 6) < 2 ? 0 : 512) + (s.dcval[b] & 0x1FF)]; };
@@ -1137,6 +1155,10 @@ static cudaError_t launch_pack_cluster_t(int threads, size_t smem, int n, const 
                                          const int *d_max_sizes, int max_size_bound, uint8_t *d_out, size_t out_stride,
                                          psxb200_bs_result_t *d_results, const BsStrLayout &str, cudaStream_t stream) {
 	auto kern = bs_pack_kernel<V3, true, STR, false, BS_PACK_MAX_THREADS, 1, BS_PACK_CLUSTER>;
+	// Programmatic stream serialisation (the kernel's set-up beside the FDCT kernel in front of it) is opt-in:
+	// measured -2 us per encode_frame_bs call, nothing inside the captured look-ahead graph, and one
+	// pathological run of the latter (263 instead of 51 us per frame) — PSXB200_PDL=1 turns it on.
+	static const bool pdl = getenv("PSXB200_PDL") != nullptr;
 	static bool configured[MAX_DEVICES];
 	{
 		int dev = 0;
@@ -1157,13 +1179,16 @@ static cudaError_t launch_pack_cluster_t(int threads, size_t smem, int n, const 
 	cfg.blockDim = dim3((unsigned)threads);
 	cfg.dynamicSmemBytes = smem;
 	cfg.stream = stream;
-	cudaLaunchAttribute attr[1];
+	cudaLaunchAttribute attr[2];
 	attr[0].id = cudaLaunchAttributeClusterDimension;
 	attr[0].val.clusterDim.x = BS_PACK_CLUSTER;
 	attr[0].val.clusterDim.y = 1;
 	attr[0].val.clusterDim.z = 1;
+	// (opt-in) the kernel's set-up overlaps the FDCT kernel in front of it (griddepcontrol.wait in the kernel)
+	attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[1].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
-	cfg.numAttrs = 1;
+	cfg.numAttrs = pdl ? 2 : 1;
 	uint32_t *no_gstream = nullptr;
 	return cudaLaunchKernelEx(&cfg, kern, d_coefs, geo.frame_stride_u4, geo.nblk, geo.ngroups, geo.nsgroups, geo.cgroups * 32,
 	                          geo.nmb, codec, d_max_sizes, max_size_bound, d_out, out_stride, d_results, no_gstream, (size_t)0, str);
