@@ -16,7 +16,7 @@ k4=$(line "uint32_t sign_lo = 0"); k5=$(line "const int count = (int)(tail"); k6
 {
 echo "Phase attribution (tools/ncu_lines.py: SASS page of the ncu report joined with the cubin's line table), strv typical content"
 echo "(noise 3, q = 2), 4096 frames per launch, kernels at the end of round 2:"
-python tools/ncu_lines.py gpurun_out/${P}_pack.ncu-rep $L 'bs_pack_kernel<false, true, false, false, 320, 4>' $a:$((b-1)):helpers-warp_sum/imad \
+python tools/ncu_lines.py gpurun_out/${P}_pack.ncu-rep $L 'bs_pack_kernel<false, true, false, false, 320, 4, 1>' $a:$((b-1)):helpers-warp_sum/imad \
   $b:$((c-1)):pricing-lists-generic $c:$((d-1)):pricing-lists-q1 $d:$((e-1)):pricing-dense $e:$((f-1)):emit-stage_dense $f:$((g-1)):emit-stage_rows \
   $g:$((h-1)):emit-BitWriter $j:$((k-1)):setup $k:$((l-1)):search-loop-body $l:$((m-1)):scan $m:$((n-1)):emit-loop $n:$((o-1)):copy-out
 python tools/ncu_lines.py gpurun_out/${P}_dct.ncu-rep $L 'bs_dct_kernel<1>' $k1:$((k2-1)):setup+zero-lists $k2:$((k3-1)):gather $k3:$((k4-1)):fdct-call \
@@ -24,7 +24,7 @@ python tools/ncu_lines.py gpurun_out/${P}_dct.ncu-rep $L 'bs_dct_kernel<1>' $k1:
 echo; echo "fdct.cuh / intrinsics lines (the transform itself) make up the rest of bs_dct_kernel."
 if [ -f gpurun_out/${P}_busy.ncu-rep ]; then
 echo; echo "BUSY instantiation of the pack kernel on noise-6 content (q = 8), tools/wave_probe.py 6 4096 (profiles/${P}_ncu_pack_busy_hard.txt):"
-python tools/ncu_lines.py gpurun_out/${P}_busy.ncu-rep $L 'bs_pack_kernel<false, true, false, true, 320, 4>' $a:$((b-1)):helpers-warp_sum/imad \
+python tools/ncu_lines.py gpurun_out/${P}_busy.ncu-rep $L 'bs_pack_kernel<false, true, false, true, 320, 4, 1>' $a:$((b-1)):helpers-warp_sum/imad \
   $d:$((e-1)):pricing-dense $e:$((f-1)):emit-stage_dense $g:$((h-1)):emit-BitWriter $i:$((j-1)):census $j:$((k-1)):setup $k:$((l-1)):search-loop-body \
   $m:$((n-1)):emit-loop $n:$((o-1)):copy-out
 fi
