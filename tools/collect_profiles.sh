@@ -31,7 +31,9 @@ fi
 } > profiles/${P}_phases.txt 2>&1
 mkdir -p profiles/${P}_sass
 for spec in "bs_dct_kernelILi1E:bs_dct_kernel_sse2" "bs_pack_kernelILb0ELb1ELb0ELb0ELi320ELi4E:bs_pack_kernel_v2_320x4" \
-            "bs_pack_kernelILb0ELb1ELb0ELb1ELi320ELi4E:bs_pack_kernel_v2_busy_320x4" "adpcm_spu_kernel:adpcm_spu_kernel"; do
+            "bs_pack_kernelILb0ELb1ELb0ELb1ELi320ELi4E:bs_pack_kernel_v2_busy_320x4" \
+            "bs_pack_kernelILb0ELb1ELb0ELb0ELi640ELi1ELi4E:bs_pack_kernel_v2_cluster4" "adpcm_spu_kernelE:adpcm_spu_kernel" \
+            "adpcm_spu_small_kernel:adpcm_spu_small_kernel"; do
   cuobjdump -sass $L | awk -v pat="${spec%%:*}" '/Function : /{p=($0 ~ pat)} p' > profiles/${P}_sass/${spec##*:}.sass
 done
 python - <<PY
