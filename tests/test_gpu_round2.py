@@ -430,15 +430,18 @@ def test_spu_multi_device_channel_split(restated):
             assert states[f * ch + c].prev1 == st.prev1
 
 
-def test_spu_host_call_cut_into_pipelined_runs(restated):
-    """A host call with thousands of whole interleave groups is cut into runs of groups that rotate
-    over several streams (capi_audio.cu): every chain must come out as if encoded alone, including
-    the partial last group, a gap between the groups and non-zero incoming states."""
-    ch, count, files = 8, 28 * 20 + 5, 1000   # runs of 464 groups (4 MB of samples each)
+@pytest.mark.parametrize("count,files,boundary", [(28 * 20 + 5, 1000, 464), (28 * 256 + 5, 260, 128)], ids=["short-chains", "long-chains"])
+def test_spu_host_call_cut_into_pipelined_runs(restated, count, files, boundary):
+    """A host call with thousands of whole interleave groups is cut into runs of groups that rotate over
+    several streams (capi_audio.cu): every chain must come out as if encoded alone, including the
+    partial last group, a buffer that ends with the last chain's last sample, a gap between the groups
+    and non-zero incoming states."""
+    ch = 8
     stride = count * ch + 24                      # groups do not touch: a few unused samples between them
     rng = np.random.default_rng(5)
     pcm = rng.integers(-32768, 32768, size=files * stride, dtype=np.int16)
     n_streams = files * ch - 3                    # last group holds 5 of its 8 chains
+    pcm = pcm[:(files - 1) * stride + (count - 1) * ch + 5]   # and the buffer ends with the last chain's last sample
     states = (pb.ChannelState * n_streams)()
     for s in range(0, n_streams, 7):
         states[s].prev1, states[s].prev2 = int(rng.integers(-3000, 3000)), int(rng.integers(-3000, 3000))
@@ -446,7 +449,8 @@ def test_spu_host_call_cut_into_pipelined_runs(restated):
     launches = pb.launch_count()
     got, states = pb.spu_encode_host(pcm, n_streams, ch, stride, count, states=states)
     assert pb.launch_count() - launches >= 2, "expected the call to be cut into several launches"
-    for s in list(range(0, n_streams, 131)) + [3711, 3712, 7423, 7424, n_streams - 1]:   # both sides of the run boundaries
+    edge = boundary * ch                          # first chain of the second run
+    for s in list(range(0, n_streams, 131)) + [edge - 1, edge, 2 * edge - 1, 2 * edge, n_streams - 1]:
         f, c = divmod(s, ch)
         st = oracle.ChannelState()
         st.prev1, st.prev2 = before[s]
