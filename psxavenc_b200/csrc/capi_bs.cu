@@ -4,6 +4,8 @@
 // bs_encode.cu. There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -194,10 +196,11 @@ static int bs_encode_chunked(psxb200_bs_encoder *enc, DeviceBuffer<uint4> &coefs
 	}
 	// Very few frames (the drop-in symbols): a cluster of CTAs per frame, see bs_pack_kernel
 	static const bool cluster_off = getenv("PSXB200_NO_CLUSTER") != nullptr;
+	static std::atomic<bool> cluster_refused{false};   // a cluster launch was turned down once (a partitioned device, say): never again
 	int cluster = 1;
 	// (clusters are placed within a GPC, so they do not tile all SMs: with half of the SMs asked for, every cluster of
 	// the launch is resident at once — 37 clusters of 4 on 148 SMs ran in two waves, 36.9 us against 32.8 us without)
-	if (2 * n * BS_PACK_CLUSTER <= enc->sm_count && !enc->pack_threads_forced && !cluster_off) {
+	if (2 * n * BS_PACK_CLUSTER <= enc->sm_count && !enc->pack_threads_forced && !cluster_off && !cluster_refused.load()) {
 		const int cl_threads = 32 * std::max(1, std::min(BS_PACK_MAX_THREADS / 32, (enc->geo.ngroups + BS_PACK_CLUSTER - 1) / BS_PACK_CLUSTER));
 		if (bs_pack_smem_bytes(enc->codec != 0, true, enc->geo, max_size_bound, cl_threads) <= BS_SMEM_BUDGET) {
 			cluster = BS_PACK_CLUSTER;
@@ -227,12 +230,18 @@ static int bs_encode_chunked(psxb200_bs_encoder *enc, DeviceBuffer<uint4> &coefs
 			str = *str_batch;
 			str.frame_base += first;   // the kernel positions every frame absolutely within the batch
 		}
-		if (cluster > 1)
-			CU_TRY(bs_launch_pack_cluster(enc->codec, threads, m, coefs.ptr, enc->geo,
-			                              (str_batch || !d_max_sizes) ? nullptr : d_max_sizes + first, max_size_bound,
-			                              str_batch ? d_out : d_out + (size_t)first * out_stride, out_stride, d_results + first,
-			                              str, stream));
-		else
+		if (cluster > 1) {
+			// launch-configuration errors come back synchronously: fall back to one CTA per frame
+			if (bs_launch_pack_cluster(enc->codec, threads, m, coefs.ptr, enc->geo,
+			                           (str_batch || !d_max_sizes) ? nullptr : d_max_sizes + first, max_size_bound,
+			                           str_batch ? d_out : d_out + (size_t)first * out_stride, out_stride, d_results + first,
+			                           str, stream) != cudaSuccess) {
+				cudaGetLastError();
+				cluster_refused.store(true);
+				cluster = 1;
+			}
+		}
+		if (cluster == 1)
 			CU_TRY(bs_launch_pack(enc->codec, threads, min_ctas, m, coefs.ptr, enc->geo,
 			                      (str_batch || !d_max_sizes) ? nullptr : d_max_sizes + first, max_size_bound,
 			                      str_batch ? d_out : d_out + (size_t)first * out_stride, out_stride, d_results + first, gstream,
